@@ -1,0 +1,90 @@
+/* include/llacuda.h -- C ABI of libllacuda.so, the B200 (sm_100a) back end for the dense
+ * linear-algebra hot path of tpapp/lla (mm / gemm!, lu, solve, cholesky).
+ *
+ * Three groups of entry points:
+ *
+ *  1. Fortran-symbol drop-ins (`dgemm_`, `dgetrf_`, ...): exactly the symbols LLA's
+ *     `blas-call` / `lapack-call` bind through `cffi:foreign-funcall`
+ *     (reference src/fortran-call.lisp:405-439: lowercase type letter + name + "_", every
+ *     argument a pointer, no hidden string-length arguments, `void` return).  All pointers are
+ *     HOST pointers valid only for the duration of the call (reference src/pinned-array.lisp:
+ *     105-141); the library stages them to the device, computes, and writes results back in
+ *     place before returning.  Select with
+ *         (defvar cl-user::*lla-configuration* '(:libraries ("libllacuda.so" "liblapack.so")))
+ *     (reference src/libraries.lisp:10-12, README.md:71-77).
+ *
+ *  2. `llacuda_<routine>` aliases of group 1 with identical signatures, for the re-pointed name
+ *     generator variant of the integration (INTEGRATION.md option B).
+ *
+ *  3. `llacuda_*_dev` entry points on DEVICE pointers (column-major, 64-bit dimensions), plus
+ *     memory / stream / timing helpers.  These are what the new device-backed Lisp methods and
+ *     the benchmark's HBM-resident leg call.
+ *
+ * Error convention (reference src/fortran-call.lisp:336-347): LAPACK-style entry points write
+ * *info = 0 on success, -k if argument k is illegal, +k for a zero pivot / non-PD minor.
+ * CUDA failures are reported out of band: *info = LLACUDA_ERR_CUDA_BASE - cudaError and a
+ * message retrievable through llacuda_last_error().  No entry point throws or longjmps.
+ */
+#ifndef LLACUDA_H
+#define LLACUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLACUDA_ERR_NO_DEVICE (-10001)
+#define LLACUDA_ERR_CUDA_BASE (-20000) /* info = BASE - cudaError_t */
+#define LLACUDA_ERR_BAD_ARG   (-10002)
+
+/* ------------------------------------------------------------------ runtime / helpers */
+int  llacuda_init(void);                       /* 0, or LLACUDA_ERR_NO_DEVICE (no CPU fallback) */
+const char* llacuda_last_error(void);
+int  llacuda_last_error_code(void);
+void llacuda_clear_error(void);
+int  llacuda_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+void* llacuda_stream(void);                    /* cudaStream_t the *_dev calls are enqueued on */
+int  llacuda_set_stream(void* cuda_stream);    /* adopt a caller-owned stream (NULL = legacy default stream) */
+int  llacuda_reset_stream(void);               /* back to the library's own stream */
+int  llacuda_synchronize(void);
+int  llacuda_last_timing(float* ms4);          /* last host-pointer call: h2d, compute, d2h, total */
+int  llacuda_malloc(void** p, size_t bytes);
+int  llacuda_free(void* p);
+int  llacuda_host_alloc(void** p, size_t bytes);   /* pinned host memory */
+int  llacuda_host_free(void* p);
+int  llacuda_memcpy_h2d(void* dst, const void* src, size_t bytes);
+int  llacuda_memcpy_d2h(void* dst, const void* src, size_t bytes);
+int  llacuda_memset(void* dst, int byte, size_t bytes);
+
+/* FP64 roof probes: sustained TFLOP/s of a register-resident DMMA (kind 0) or DFMA (kind 1)
+ * loop on every SM; the roofline denominator bench.py reports against (MEASURED_PEAKS.json
+ * holds no FP64 figure). */
+int  llacuda_probe_fp64_peak(int kind, int iters, double* tflops, float* ms);
+
+/* ------------------------------------------------------------------ device-pointer API */
+/* op: 'N', 'T' or 'C'.  tri: 0 full, 1 only tiles/elements with row<=col, 2 only row>=col. */
+int llacuda_dgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, double alpha,
+                      const double* A, int64_t lda, const double* B, int64_t ldb,
+                      double beta, double* C, int64_t ldc);
+int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, double alpha,
+                           const double* A, int64_t lda, const double* B, int64_t ldb,
+                           double beta, double* C, int64_t ldc, int tri);
+int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
+                      const void* A, int64_t lda, const void* B, int64_t ldb,
+                      const double* beta2, void* C, int64_t ldc);
+
+/* ------------------------------------------------------------------ Fortran drop-ins */
+/* reference call sites: mm  src/linear-algebra.lisp:50-54 ; gemm!  src/blas.lisp:56-63 */
+void dgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+            const double* alpha, const double* a, const int* lda, const double* b, const int* ldb,
+            const double* beta, double* c, const int* ldc);
+void llacuda_dgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+                   const double* alpha, const double* a, const int* lda, const double* b,
+                   const int* ldb, const double* beta, double* c, const int* ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLACUDA_H */

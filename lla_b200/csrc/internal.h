@@ -1,0 +1,88 @@
+// lla_b200/csrc/internal.h -- internal declarations shared by the llacuda translation units.
+// Nothing in here crosses the C ABI; the public surface is include/llacuda.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuComplex.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace llacuda {
+
+// ------------------------------------------------------------------ errors
+// CUDA failures never masquerade as LAPACK INFO codes:
+// they are recorded here and surfaced through llacuda_last_error().
+void set_error(const char* file, int line, const char* what, int code);
+int  record_cuda_error(cudaError_t e, const char* file, int line);
+
+#define LLA_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) return ::llacuda::record_cuda_error(_e, __FILE__, __LINE__); \
+  } while (0)
+
+#define LLA_TRY(call)                     \
+  do {                                    \
+    int _r = (call);                      \
+    if (_r != 0) return _r;               \
+  } while (0)
+
+// ------------------------------------------------------------------ context
+struct Context {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;     // main compute stream
+  cudaStream_t aux = nullptr;        // panel / look-ahead stream
+  cudaStream_t h2d = nullptr;        // staging streams
+  cudaStream_t d2h = nullptr;
+  cudaEvent_t ev[8] = {};
+  // grow-only device workspace (factorisation scratch: pivots, info, barrier words, T inverses)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // pinned staging ring for pageable host operands
+  void* pin[4] = {};
+  size_t pin_bytes = 0;
+  // timing of the last host-pointer call (ms): [0]=h2d [1]=compute [2]=d2h [3]=total
+  float last_ms[4] = {};
+};
+Context* ctx();                       // lazily initialised, per process, current device
+int ensure_workspace(size_t bytes);   // ctx()->ws valid for >= bytes afterwards
+
+// device scratch allocations that live for one call
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n);
+  ~DevBuf();
+};
+
+// ------------------------------------------------------------------ GEMM (gemm_f64.cu)
+enum GemmTri { TRI_FULL = 0, TRI_UPPER = 1, TRI_LOWER = 2 };
+// op codes: 0 = N, 1 = T, 2 = C (== T for real types)
+int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha,
+              const double* A, int64_t lda, const double* B, int64_t ldb,
+              double beta, double* C, int64_t ldc, int tri, cudaStream_t st);
+int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
+              const cuDoubleComplex* A, int64_t lda, const cuDoubleComplex* B, int64_t ldb,
+              cuDoubleComplex beta, cuDoubleComplex* C, int64_t ldc, int tri, cudaStream_t st);
+
+// ------------------------------------------------------------------ TRSM (trsm_f64.cu), left side only
+// solves op(T) X = alpha B in place; T is m x m triangular, B is m x n
+int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n, double alpha,
+                   const double* T, int64_t ldt, double* B, int64_t ldb, cudaStream_t st);
+
+// ------------------------------------------------------------------ factorisations
+int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st);
+int dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv,
+               bool forward, cudaStream_t st);
+int dgetrs_dev(int op, int64_t n, int64_t nrhs, const double* A, int64_t lda, const int* ipiv,
+               double* B, int64_t ldb, cudaStream_t st);
+int dpotrf_dev(bool upper, int64_t n, double* A, int64_t lda, int* info_dev, cudaStream_t st);
+int dpotrs_dev(bool upper, int64_t n, int64_t nrhs, const double* A, int64_t lda,
+               double* B, int64_t ldb, cudaStream_t st);
+
+// ------------------------------------------------------------------ layout kernels (transpose.cu)
+int dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out, int64_t ldout,
+                   cudaStream_t st);   // out[c + r*ldout] = in[r + c*ldin]
+int dtranspose_inplace_dev(int64_t n, double* A, int64_t lda, cudaStream_t st);
+
+}  // namespace llacuda

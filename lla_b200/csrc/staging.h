@@ -1,0 +1,37 @@
+// lla_b200/csrc/staging.h -- host <-> device staging for the Fortran drop-in entry points.
+//
+// LLA hands the library HOST pointers that are only valid for the duration of the call: either
+// SBCL heap vectors pinned in place (pageable memory, reference src/pinned-array.lisp:135-141)
+// or foreign scratch (src/pinned-array.lisp:105-109).  A matrix operand (rows x cols, leading
+// dimension ldh) is copied into a device buffer whose leading dimension is padded to an even
+// number of elements so that every column starts 16-byte aligned for the cp.async loaders.
+#pragma once
+#include "internal.h"
+
+namespace llacuda {
+
+struct Staged {
+  DevBuf buf;
+  int64_t ld = 0;
+  int64_t rows = 0, cols = 0;
+  size_t es = 0;
+  template <class T> T* ptr() { return (T*)buf.p; }
+};
+
+int stage_alloc(Staged& s, int64_t rows, int64_t cols, size_t es);
+int stage_upload(Staged& s, const void* host, int64_t ldh, cudaStream_t st);
+// upload only the part of the matrix selected by tri (0 all, 1 upper incl. diagonal, 2 lower)
+int stage_download(const Staged& s, void* host, int64_t ldh, cudaStream_t st);
+
+// wall-clock phases of one host-pointer call, written to ctx()->last_ms
+struct PhaseTimer {
+  cudaEvent_t e[4];
+  cudaStream_t st;
+  bool ok = false;
+  explicit PhaseTimer(cudaStream_t s);
+  ~PhaseTimer();
+  void mark(int i);   // 0 start, 1 after h2d, 2 after compute, 3 after d2h
+  void finish();      // synchronises and stores the four durations
+};
+
+}  // namespace llacuda

@@ -1,0 +1,46 @@
+"""Thin typed bindings of the llacuda_*_dev entry points (device pointers, column-major).
+
+Torch is used only as the owner of device memory and streams: a column-major m x n matrix with
+leading dimension ld is a torch tensor of shape (n, ld) whose row j is column j.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _lib
+
+_i64 = ctypes.c_int64
+_dbl = ctypes.c_double
+_vp = ctypes.c_void_p
+_chr = ctypes.c_char
+
+
+def _sig(name, argtypes):
+    f = getattr(_lib.lib(), name)
+    f.argtypes = argtypes
+    f.restype = ctypes.c_int
+    return f
+
+
+def use_torch_stream():
+    """Enqueue every *_dev call on torch's current stream so torch.cuda.Event timing sees it."""
+    import torch
+    _lib.check(_sig("llacuda_set_stream", [_vp])(torch.cuda.current_stream().cuda_stream), "set_stream")
+
+
+def colmajor(t):
+    """(data_ptr, ld) of a torch tensor interpreted as column-major storage (shape (n, ld))."""
+    assert t.is_cuda and t.is_contiguous()
+    return _vp(t.data_ptr()), t.shape[-1]
+
+
+def dgemm(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri=0):
+    f = _sig("llacuda_dsyrk_like_dev", [_chr, _chr, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64, ctypes.c_int])
+    _lib.check(f(opa.encode(), opb.encode(), m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri), "dgemm_dev")
+
+
+def probe_fp64_peak(kind, iters=20000):
+    tf, ms = ctypes.c_double(0), ctypes.c_float(0)
+    f = _sig("llacuda_probe_fp64_peak", [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)])
+    _lib.check(f(kind, iters, ctypes.byref(tf), ctypes.byref(ms)), "probe")
+    return tf.value, ms.value

@@ -1,0 +1,335 @@
+"""Host-side mirror of LLA's user API for the hot path, on NumPy row-major arrays.
+
+There is no Common Lisp in the build image, so this module plays the role of the Lisp layers
+L7..L3 (reference src/linear-algebra.lisp, src/blas.lisp, src/factorizations.lisp,
+src/fortran-call.lisp, src/pinned-array.lisp, src/foreign-memory.lisp) with the same names,
+argument meaning and error behaviour, and issues *exactly* the Fortran-ABI calls LLA issues --
+but into libllacuda.so.  It is what the parity tests drive; the Lisp glue that does the same from
+SBCL lives under lisp/ (see INTEGRATION.md).
+
+Lisp arrays are row-major; "share" means the NumPy buffer is passed untouched (what SBCL does by
+pinning, src/pinned-array.lisp:124-141), "transpose" means a column-major copy
+(src/foreign-memory.lisp:211-255).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+# internal type codes, reference src/types.lisp:22-26
+SINGLE, DOUBLE, COMPLEX_SINGLE, COMPLEX_DOUBLE = 0, 1, 2, 3
+_DTYPES = {SINGLE: np.float32, DOUBLE: np.float64, COMPLEX_SINGLE: np.complex64, COMPLEX_DOUBLE: np.complex128}
+_LETTER = {SINGLE: "s", DOUBLE: "d", COMPLEX_SINGLE: "c", COMPLEX_DOUBLE: "z"}
+
+
+# ------------------------------------------------------------------ conditions (src/conditions.lisp)
+class LapackInvalidArgument(Exception):
+    """reference src/conditions.lisp:27-33 (INFO < 0), slot POSITION."""
+
+    def __init__(self, position):
+        super().__init__(f"LAPACK: argument {position} illegal")
+        self.position = position
+
+
+class LapackFailure(Exception):
+    """reference src/conditions.lisp:35-43 (INFO > 0), slot INFO."""
+
+    def __init__(self, info):
+        super().__init__(f"LAPACK failure, INFO={info}")
+        self.info = info
+
+
+class LapackSingularMatrix(LapackFailure):
+    """reference src/conditions.lisp:41-43."""
+
+
+class LlaIncompatibleDimensions(Exception):
+    """reference src/conditions.lisp:45-47."""
+
+
+# ------------------------------------------------------------------ types (src/types.lisp)
+def array_float_type(a) -> int:
+    """reference src/types.lisp:69-80; integer / rational element types classify as double."""
+    dt = np.asarray(a).dtype
+    if dt == np.float32:
+        return SINGLE
+    if dt == np.complex64:
+        return COMPLEX_SINGLE
+    if dt == np.complex128:
+        return COMPLEX_DOUBLE
+    return DOUBLE
+
+
+def common_float_type(*arrays) -> int:
+    """reference src/types.lisp:82-89: LOGIOR of the codes."""
+    code = 0
+    for a in arrays:
+        code |= array_float_type(a)
+    return code
+
+
+# ------------------------------------------------------------------ marshalling (L3/L4)
+def _as_memory(a, tcode) -> np.ndarray:
+    """share when the array already has the target element type and is a simple (contiguous)
+    array, else element-wise coercing copy (src/pinned-array.lisp:124-128, src/foreign-memory.lisp:168-182)."""
+    a = np.asarray(a)
+    if np.iscomplexobj(a) and tcode in (SINGLE, DOUBLE):
+        raise TypeError("cannot coerce a complex array to a real type")
+    if a.dtype == _DTYPES[tcode] and a.flags.c_contiguous:
+        return a
+    return np.array(a, dtype=_DTYPES[tcode], order="C", copy=True)
+
+
+def _transposed_to_memory(a, tcode) -> np.ndarray:
+    """reference src/foreign-memory.lisp:211-230: row-major matrix -> column-major image."""
+    a = np.asarray(a)
+    if np.iscomplexobj(a) and tcode in (SINGLE, DOUBLE):
+        raise TypeError("cannot coerce a complex array to a real type")
+    if a.ndim == 1:
+        return np.array(a, dtype=_DTYPES[tcode], order="C", copy=True)
+    return np.array(a.T, dtype=_DTYPES[tcode], order="C", copy=True)
+
+
+def _transposed_from_memory(mem, shape) -> np.ndarray:
+    """reference src/foreign-memory.lisp:232-255."""
+    if len(shape) == 1:
+        return mem.reshape(shape).copy()
+    return np.ascontiguousarray(mem.reshape(shape[1], shape[0]).T)
+
+
+def dimensions_as_matrix(a, orientation):
+    """reference src/linear-algebra.lisp:18-26."""
+    a = np.asarray(a)
+    if a.ndim == 1:
+        return (1, a.shape[0], True) if orientation == "row" else (a.shape[0], 1, True)
+    if a.ndim == 2:
+        return a.shape[0], a.shape[1], False
+    raise ValueError("array rank must be 1 or 2")
+
+
+def _int(v):
+    return ctypes.byref(ctypes.c_int(int(v)))
+
+
+def _chr(c):
+    return ctypes.byref(ctypes.c_char(c.encode()))
+
+
+def _atom(v, tcode):
+    a = np.array([v], dtype=_DTYPES[tcode])
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _fn(tcode, name):
+    """reference src/fortran-call.lisp:405-416: type letter + routine name + underscore."""
+    f = getattr(_lib.lib(), f"{_LETTER[tcode]}{name}_")
+    f.restype = None
+    return f
+
+
+def _check_device_error():
+    if _lib.lib().llacuda_last_error_code() != 0:
+        msg = _lib.last_error()
+        _lib.lib().llacuda_clear_error()
+        raise _lib.LlacudaError(msg)
+
+
+def _check_info(info, condition=LapackFailure):
+    """reference src/fortran-call.lisp:336-347."""
+    if info <= -10000:
+        msg = _lib.last_error()
+        _lib.lib().llacuda_clear_error()
+        raise _lib.LlacudaError(f"device failure (info={info}): {msg}")
+    if info < 0:
+        raise LapackInvalidArgument(-info)
+    if info > 0 and condition is not None:
+        raise condition(info)
+
+
+# ------------------------------------------------------------------ mm / gemm!
+def mm(a, b):
+    """reference src/linear-algebra.lisp:39-54."""
+    a, b = np.asarray(a), np.asarray(b)
+    t = common_float_type(a, b)
+    a0, a1, av = dimensions_as_matrix(a, "row")
+    b0, b1, bv = dimensions_as_matrix(b, "column")
+    if av and bv:
+        raise ValueError("MM called with two vectors.  Use OUTER or DOT instead.")
+    if a1 != b0:
+        raise AssertionError("Incompatible dimensions.")
+    am, bm = _as_memory(a, t), _as_memory(b, t)
+    c = np.zeros(a0 * b1 if (av or bv) else (a0, b1), dtype=_DTYPES[t])
+    _one, pone = _atom(1, t)
+    _zero, pzero = _atom(0, t)
+    _fn(t, "gemm")(_chr("N"), _chr("N"), _int(b1), _int(a0), _int(b0), pone, _ptr(bm), _int(b1),
+                   _ptr(am), _int(a1), pzero, _ptr(c), _int(b1))
+    _check_device_error()
+    return c
+
+
+def gemm(alpha, a, b, beta, c, transpose_a=False, transpose_b=False, m=None, n=None, k=None,
+         lda=None, ldb=None, ldc=None):
+    """gemm!, reference src/blas.lisp:7-63.  C is updated in place and returned."""
+    a, b = np.asarray(a), np.asarray(b)
+    t = common_float_type(a, b)
+    m = c.shape[0] if m is None else m
+    n = c.shape[1] if n is None else n
+    k = (a.shape[0] if transpose_a else a.shape[1]) if k is None else k
+    lda = a.shape[1] if lda is None else lda
+    ldb = b.shape[1] if ldb is None else ldb
+    ldc = c.shape[1] if ldc is None else ldc
+    if transpose_a:
+        assert m <= lda and lda * k <= a.size
+    else:
+        assert k <= lda and m * lda <= a.size
+    if transpose_b:
+        assert k <= ldb and ldb * n <= b.size
+    else:
+        assert n <= ldb and k * ldb <= b.size
+    assert n <= ldc and m * ldc <= c.size
+    am, bm = _as_memory(a, t), _as_memory(b, t)
+    cm = _as_memory(c, t)
+    _al, pal = _atom(alpha, t)
+    _bt, pbt = _atom(beta, t)
+    _fn(t, "gemm")(_chr("C" if transpose_b else "N"), _chr("C" if transpose_a else "N"),
+                   _int(n), _int(m), _int(k), pal, _ptr(bm), _int(ldb), _ptr(am), _int(lda),
+                   pbt, _ptr(cm), _int(ldc))
+    _check_device_error()
+    if cm is not c:
+        c[...] = cm  # copy-back rule, src/pinned-array.lisp:90-103
+    return c
+
+
+# ------------------------------------------------------------------ lu / solve
+class LU:
+    """reference src/factorizations.lisp:47-52 with the ipiv-mixin of :7-13."""
+
+    def __init__(self, lu, ipiv_internal):
+        self.lu, self.ipiv_internal = lu, ipiv_internal
+
+
+def lu(a) -> LU:
+    """reference src/linear-algebra.lisp:225-234: GETRF on a transposed copy; INFO>0 ignored."""
+    a = np.asarray(a)
+    t = common_float_type(a)
+    a0, a1 = a.shape
+    mem = _transposed_to_memory(a, t)
+    ipiv_internal = np.zeros(min(a0, a1), dtype=np.int32)
+    info = ctypes.c_int(0)
+    _fn(t, "getrf")(_int(a0), _int(a1), _ptr(mem), _int(a0), _ptr(ipiv_internal), ctypes.byref(info))
+    _check_info(info.value, None)
+    return LU(_transposed_from_memory(mem, (a0, a1)), ipiv_internal)
+
+
+class Cholesky:
+    """reference src/factorizations.lisp:130-136: LEFT is the lower-triangular left square root."""
+
+    def __init__(self, left):
+        self.left = left
+
+
+def solve(a, b):
+    """reference src/linear-algebra.lisp:257-301, dispatching on the class of A like the generic function."""
+    b = np.asarray(b)
+    if isinstance(a, LU):
+        lu0, lu1 = a.lu.shape
+        b0, b1, _ = dimensions_as_matrix(b, "column")
+        if not (lu0 == lu1 == b0):
+            raise LlaIncompatibleDimensions()
+        t = common_float_type(a.lu, b)
+        amem = _transposed_to_memory(a.lu, t)
+        bmem = _transposed_to_memory(b, t)
+        info = ctypes.c_int(0)
+        _fn(t, "getrs")(_chr("N"), _int(lu0), _int(b1), _ptr(amem), _int(lu0), _ptr(a.ipiv_internal),
+                        _ptr(bmem), _int(lu0), ctypes.byref(info))
+        _check_info(info.value)
+        return _transposed_from_memory(bmem, b.shape)
+    if isinstance(a, Cholesky):
+        l = a.left
+        a0, a1 = l.shape
+        b0, b1, _ = dimensions_as_matrix(b, "column")
+        if not (a0 == a1 == b0):
+            raise LlaIncompatibleDimensions()
+        t = common_float_type(l, b)
+        amem = _as_memory(l, t)  # shared, read-only
+        bmem = _transposed_to_memory(b, t)
+        info = ctypes.c_int(0)
+        _fn(t, "potrs")(_chr("U"), _int(a0), _int(b1), _ptr(amem), _int(a0), _ptr(bmem), _int(b0),
+                        ctypes.byref(info))
+        _check_info(info.value)
+        return _transposed_from_memory(bmem, b.shape)
+    a = np.asarray(a)
+    a0, a1 = a.shape
+    b0, b1, _ = dimensions_as_matrix(b, "column")
+    if not (a0 == a1 == b0):
+        raise LlaIncompatibleDimensions()
+    t = common_float_type(a, b)
+    amem = _transposed_to_memory(a, t)
+    bmem = _transposed_to_memory(b, t)
+    ipiv_scratch = np.zeros(a0, dtype=np.int32)  # (&work a0 +integer+), discarded
+    info = ctypes.c_int(0)
+    _fn(t, "gesv")(_int(a0), _int(b1), _ptr(amem), _int(a0), _ptr(ipiv_scratch), _ptr(bmem), _int(a0),
+                   ctypes.byref(info))
+    _check_info(info.value)
+    return _transposed_from_memory(bmem, b.shape)
+
+
+def cholesky(a) -> Cholesky:
+    """reference src/linear-algebra.lisp:666-674: POTRF('U') on an untransposed copy of the
+    row-major elements; only the row-major lower triangle is read, and the result is wrapped as a
+    lower-triangular matrix (the strict upper triangle is masked)."""
+    a = np.asarray(a)
+    a0, a1 = a.shape
+    if a0 != a1:
+        raise LlaIncompatibleDimensions()
+    t = common_float_type(a)
+    mem = np.array(a, dtype=_DTYPES[t], order="C", copy=True)  # force-copy: input is not output
+    info = ctypes.c_int(0)
+    _fn(t, "potrf")(_chr("U"), _int(a0), _ptr(mem), _int(a0), ctypes.byref(info))
+    _check_info(info.value)
+    return Cholesky(np.tril(mem))
+
+
+# ------------------------------------------------------------------ factorization post-processing
+def ipiv(ipiv_internal) -> np.ndarray:
+    """reference src/factorizations.lisp:15-28: LAPACK swap sequence -> 0-based permutation."""
+    n = len(ipiv_internal)
+    it = np.arange(n, dtype=np.int64)
+    for index in range(n):
+        p = int(ipiv_internal[index]) - 1
+        if p != index:
+            it[index], it[p] = it[p], it[index]
+    return it
+
+
+def ipiv_inverse(ipiv_internal) -> np.ndarray:
+    """reference src/factorizations.lisp:30-43."""
+    p = ipiv(ipiv_internal)
+    inv = np.zeros(len(p), dtype=np.int64)
+    inv[p] = np.arange(len(p))
+    return inv
+
+
+def lu_u(f: LU) -> np.ndarray:
+    """reference src/factorizations.lisp:54-56."""
+    return np.triu(f.lu)
+
+
+def lu_l(f: LU) -> np.ndarray:
+    """reference src/factorizations.lisp:58-65 (unit diagonal forced)."""
+    l = np.tril(f.lu).copy()
+    for i in range(min(l.shape)):
+        l[i, i] = 1
+    return l
+
+
+def permutations(ipiv_internal) -> int:
+    """reference src/factorizations.lisp:143-151."""
+    return int(sum(1 for i, p in enumerate(ipiv_internal, start=1) if p != i))

@@ -1,0 +1,113 @@
+"""GPU parity: DGEMM through the Fortran drop-in (`dgemm_`, host pointers) against the CPU oracle.
+
+Cases restated from the reference's own tests:
+  mm goldens           tests/linear-algebra.lisp:9-29
+  gemm! randomized     tests/blas.lisp:19-46   (integer-valued operands in padded "sloppy" arrays)
+plus seeded random cases at sizes the oracle finishes in seconds and BASELINE configs[0] (n=1024).
+Tolerance (north_star "elementwise error <= k * eps * ||A|| ||B||"): with a_i the i-th row of
+op(A) and b_j the j-th column of op(B),  |C_ij - Cref_ij| <= k * eps * ||a_i||_2 ||b_j||_2  with
+k = 4*sqrt(K) (the rigorous worst case is k = K; both sides of the comparison carry rounding).
+"""
+import numpy as np
+import pytest
+
+from lla_b200 import lla as L
+from oracle import lla_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+def gemm_tol(opa_a, opb_b, K, scale=1.0):
+    """k*eps*||a_i|| ||b_j|| matrix for op(A) (m x K) and op(B) (K x n)."""
+    ra = np.linalg.norm(opa_a, axis=1)[:, None]
+    cb = np.linalg.norm(opb_b, axis=0)[None, :]
+    return 4 * np.sqrt(max(K, 1)) * EPS * scale * ra * cb + 1e-300
+
+
+def test_mm_goldens():
+    a = np.array([[1, 2], [3, 4], [5, 6]], dtype=np.float64)
+    b2 = np.array([1, 2], dtype=np.float64)
+    b3 = np.array([1, 2, 3], dtype=np.float64)
+    assert np.array_equal(L.mm(a, np.eye(2)), a)
+    assert np.array_equal(L.mm(np.eye(3), a), a)
+    r = L.mm(a, b2)
+    assert r.shape == (3,) and np.array_equal(r, [5, 11, 17])
+    r = L.mm(b3, a)
+    assert r.shape == (2,) and np.array_equal(r, [22, 28])
+    with pytest.raises(Exception):
+        L.mm(a, b3)
+    with pytest.raises(Exception):
+        L.mm(b2, b3)
+
+
+def sloppy(rng, h, w):
+    full = rng.integers(0, 100, (h + rng.integers(0, 3), w + rng.integers(0, 3))).astype(np.float64)
+    return full
+
+
+def test_gemm_randomized_like_reference():
+    rng = np.random.default_rng(11)
+    be = O.netlib()
+    for _ in range(100):
+        m, n, k = (int(v) for v in rng.integers(1, 11, 3))
+        ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        a_ = sloppy(rng, *((k, m) if ta else (m, k)))
+        b_ = sloppy(rng, *((n, k) if tb else (k, n)))
+        c_ = sloppy(rng, m, n)
+        alpha, beta = rng.uniform(0, 10), rng.uniform(0, 10)
+        want = O.gemm(alpha, a_, b_, beta, c_.copy(), be, transpose_a=ta, transpose_b=tb, m=m, n=n, k=k)
+        got = L.gemm(alpha, a_, b_, beta, c_.copy(), transpose_a=ta, transpose_b=tb, m=m, n=n, k=k)
+        # integer operands: the products are exact, only alpha/beta scaling rounds -> 2 ulp
+        assert np.allclose(got, want, rtol=4 * EPS, atol=0), (m, n, k, ta, tb)
+        # cells outside the logical m x n block must be untouched
+        mask = np.ones_like(c_, dtype=bool)
+        mask[:m, :n] = False
+        assert np.array_equal(got[mask], c_[mask])
+
+
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (64, 64, 64), (129, 67, 33), (200, 31, 250), (33, 300, 17), (257, 255, 130)])
+def test_gemm_shapes_vs_oracle(ta, tb, m, n, k):
+    rng = np.random.default_rng(m * 1000 + n * 10 + k)
+    a = rng.uniform(-1, 1, (k, m) if ta else (m, k))
+    b = rng.uniform(-1, 1, (n, k) if tb else (k, n))
+    c = rng.uniform(-1, 1, (m, n))
+    for alpha, beta in ((1.0, 0.0), (0.7, 1.3), (0.0, 0.5), (2.0, 1.0)):
+        want = O.gemm(alpha, a, b, beta, c.copy(), O.openblas(), transpose_a=ta, transpose_b=tb)
+        got = L.gemm(alpha, a, b, beta, c.copy(), transpose_a=ta, transpose_b=tb)
+        tol = gemm_tol(a.T if ta else a, b.T if tb else b, k, abs(alpha)) + 4 * EPS * abs(beta) * np.abs(c)
+        assert np.all(np.abs(got - want) <= tol)
+
+
+def test_beta_zero_does_not_read_c():
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(-1, 1, (40, 30)), rng.uniform(-1, 1, (30, 20))
+    c = np.full((40, 20), np.nan)
+    got = L.gemm(1.0, a, b, 0.0, c)
+    assert np.all(np.isfinite(got))
+    assert np.allclose(got, a @ b, atol=30 * 4 * EPS)
+
+
+def test_mm_config0_1024():
+    """BASELINE configs[0]: (lla:mm a b) 1024x1024 double, (i) integer operands => exact, (ii) U[0,1)."""
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 100, (1024, 1024)).astype(np.float64)
+    b = rng.integers(0, 100, (1024, 1024)).astype(np.float64)
+    assert np.array_equal(L.mm(a, b), O.mm(a, b, O.openblas()))
+    a, b = rng.uniform(0, 1, (1024, 1024)), rng.uniform(0, 1, (1024, 1024))
+    got, want = L.mm(a, b), O.mm(a, b, O.openblas())
+    assert np.all(np.abs(got - want) <= gemm_tol(a, b, 1024))
+
+
+def test_mm_linearity_large():
+    """size-independent property at a size the oracle would not finish quickly:
+    (A1 + A2) B == A1 B + A2 B up to rounding, and mm(A, I) == A exactly."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    a1, a2, b = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    lhs = L.mm(a1 + a2, b)
+    rhs = L.mm(a1, b) + L.mm(a2, b)
+    assert np.all(np.abs(lhs - rhs) <= 2 * gemm_tol(np.abs(a1) + np.abs(a2), b, n))
+    assert np.array_equal(L.mm(a1, np.eye(n)), a1)
