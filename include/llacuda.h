@@ -71,9 +71,21 @@ int llacuda_dgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, doubl
 int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, double alpha,
                            const double* A, int64_t lda, const double* B, int64_t ldb,
                            double beta, double* C, int64_t ldc, int tri);
-int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
-                      const void* A, int64_t lda, const void* B, int64_t ldb,
-                      const double* beta2, void* C, int64_t ldc);
+
+/* factorisations and solves on device-resident column-major operands; ipiv_dev / info_dev are
+ * DEVICE pointers (int32), written asynchronously on llacuda_stream() */
+int llacuda_dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv_dev, int* info_dev);
+int llacuda_dgetrs_dev(char trans, int64_t n, int64_t nrhs, const double* A, int64_t lda,
+                       const int* ipiv_dev, double* B, int64_t ldb);
+int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv_dev, double* B,
+                      int64_t ldb, int* info_dev);
+int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, int* info_dev);
+int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const double* A, int64_t lda, double* B,
+                       int64_t ldb);
+/* out[c + r*ldout] = in[r + c*ldin]: the device-side replacement of LLA's
+ * transpose-matrix-to/from-memory (reference src/foreign-memory.lisp:211-255) */
+int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out,
+                           int64_t ldout);
 
 /* ------------------------------------------------------------------ Fortran drop-ins */
 /* reference call sites: mm  src/linear-algebra.lisp:50-54 ; gemm!  src/blas.lisp:56-63 */
@@ -83,6 +95,28 @@ void dgemm_(const char* transa, const char* transb, const int* m, const int* n, 
 void llacuda_dgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
                    const double* alpha, const double* a, const int* lda, const double* b,
                    const int* ldb, const double* beta, double* c, const int* ldc);
+
+/* lu: src/linear-algebra.lisp:227-234 */
+void dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+/* solve (lu): src/linear-algebra.lisp:269-276 */
+void dgetrs_(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda,
+             const int* ipiv, double* b, const int* ldb, int* info);
+/* solve (array array): src/linear-algebra.lisp:282-289 */
+void dgesv_(const int* n, const int* nrhs, double* a, const int* lda, int* ipiv, double* b,
+            const int* ldb, int* info);
+/* cholesky: src/linear-algebra.lisp:670-674 */
+void dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+/* solve (cholesky): src/linear-algebra.lisp:296-301 */
+void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda,
+             double* b, const int* ldb, int* info);
+void llacuda_dgetrf(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+void llacuda_dgetrs(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda,
+                    const int* ipiv, double* b, const int* ldb, int* info);
+void llacuda_dgesv(const int* n, const int* nrhs, double* a, const int* lda, int* ipiv, double* b,
+                   const int* ldb, int* info);
+void llacuda_dpotrf(const char* uplo, const int* n, double* a, const int* lda, int* info);
+void llacuda_dpotrs(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda,
+                    double* b, const int* ldb, int* info);
 
 #ifdef __cplusplus
 }

@@ -88,3 +88,273 @@ LLA_EXPORT void llacuda_dgemm(const char* transa, const char* transb, const int*
                               const int* ldb, const double* beta, double* c, const int* ldc) {
   dgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }
+
+// ------------------------------------------------------------------ LAPACK drop-ins
+static inline int64_t max1(int64_t x) { return x > 1 ? x : 1; }
+
+// reads the device INFO word back; a CUDA failure overrides it with the out-of-band code
+
+static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, int* ipiv, int* info) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa;
+  DevBuf piv, inf;
+  int64_t mn = m < n ? m : n;
+  LLA_TRY(stage_alloc(sa, m, n, sizeof(double)));
+  LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(mn)));
+  LLA_TRY(inf.alloc(sizeof(int)));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  tm.mark(1);
+  LLA_TRY(dgetrf_dev(m, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st));
+  tm.mark(2);
+  LLA_TRY(stage_download(sa, a, lda, st));
+  if (mn > 0) LLA_CUDA(cudaMemcpyAsync(ipiv, piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
+  LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: lu, src/linear-algebra.lisp:227-234 */
+LLA_EXPORT void dgetrf_(const int* m_, const int* n_, double* a, const int* lda_, int* ipiv, int* info) {
+  int64_t m = *m_, n = *n_, lda = *lda_;
+  *info = 0;
+  if (m < 0) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (lda < max1(m)) { *info = -4; return; }
+  if (m == 0 || n == 0) return;
+  int rc = dgetrf_host(m, n, a, lda, ipiv, info);
+  if (rc != 0) *info = rc;
+}
+
+static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t lda, const int* ipiv, double* b,
+                       int64_t ldb) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa, sb;
+  DevBuf piv;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
+  LLA_TRY(piv.alloc(sizeof(int) * (size_t)n));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  LLA_TRY(stage_upload(sb, b, ldb, st));
+  LLA_CUDA(cudaMemcpyAsync(piv.p, ipiv, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+  tm.mark(1);
+  LLA_TRY(dgetrs_dev(op, n, nrhs, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st));
+  tm.mark(2);
+  LLA_TRY(stage_download(sb, b, ldb, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: solve (lu), src/linear-algebra.lisp:269-276 */
+LLA_EXPORT void dgetrs_(const char* trans, const int* n_, const int* nrhs_, const double* a, const int* lda_,
+                        const int* ipiv, double* b, const int* ldb_, int* info) {
+  int op = opcode(*trans);
+  int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  *info = 0;
+  if (op < 0) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (nrhs < 0) { *info = -3; return; }
+  if (lda < max1(n)) { *info = -5; return; }
+  if (ldb < max1(n)) { *info = -8; return; }
+  if (n == 0 || nrhs == 0) return;
+  int rc = dgetrs_host(op, n, nrhs, a, lda, ipiv, b, ldb);
+  if (rc != 0) *info = rc;
+}
+
+static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, int* ipiv, double* b, int64_t ldb,
+                      int* info) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa, sb;
+  DevBuf piv, inf;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
+  LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(n)));
+  LLA_TRY(inf.alloc(sizeof(int)));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  LLA_TRY(stage_upload(sb, b, ldb, st));
+  tm.mark(1);
+  LLA_TRY(dgetrf_dev(n, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st));
+  // DGESV solves only when the factorisation reported INFO = 0: the INFO word is the abort flag
+  LLA_TRY(dgetrs_dev(0, n, nrhs, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st,
+                     (const int*)inf.p));
+  tm.mark(2);
+  LLA_TRY(stage_download(sa, a, lda, st));
+  LLA_TRY(stage_download(sb, b, ldb, st));
+  LLA_CUDA(cudaMemcpyAsync(ipiv, piv.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: solve (array array), src/linear-algebra.lisp:282-289 */
+LLA_EXPORT void dgesv_(const int* n_, const int* nrhs_, double* a, const int* lda_, int* ipiv, double* b,
+                       const int* ldb_, int* info) {
+  int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  *info = 0;
+  if (n < 0) { *info = -1; return; }
+  if (nrhs < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (ldb < max1(n)) { *info = -7; return; }
+  if (n == 0) return;
+  int rc = dgesv_host(n, nrhs, a, lda, ipiv, b, ldb, info);
+  if (rc != 0) *info = rc;
+}
+
+static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, int* info) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa;
+  DevBuf inf;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(inf.alloc(sizeof(int)));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  tm.mark(1);
+  LLA_TRY(dpotrf_dev(upper, n, sa.ptr<double>(), sa.ld, (int*)inf.p, st));
+  tm.mark(2);
+  // the other triangle is never written on the device, so copying the whole block back
+  // leaves the caller's bytes there unchanged
+  LLA_TRY(stage_download(sa, a, lda, st));
+  LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: cholesky, src/linear-algebra.lisp:670-674 (always UPLO = 'U') */
+LLA_EXPORT void dpotrf_(const char* uplo, const int* n_, double* a, const int* lda_, int* info) {
+  int64_t n = *n_, lda = *lda_;
+  bool upper = (*uplo == 'U' || *uplo == 'u');
+  bool lower = (*uplo == 'L' || *uplo == 'l');
+  *info = 0;
+  if (!upper && !lower) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (n == 0) return;
+  int rc = dpotrf_host(upper, n, a, lda, info);
+  if (rc != 0) *info = rc;
+}
+
+static int dpotrs_host(bool upper, int64_t n, int64_t nrhs, const double* a, int64_t lda, double* b, int64_t ldb) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa, sb;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  LLA_TRY(stage_upload(sb, b, ldb, st));
+  tm.mark(1);
+  LLA_TRY(dpotrs_dev(upper, n, nrhs, sa.ptr<double>(), sa.ld, sb.ptr<double>(), sb.ld, st));
+  tm.mark(2);
+  LLA_TRY(stage_download(sb, b, ldb, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: solve (cholesky), src/linear-algebra.lisp:296-301 */
+LLA_EXPORT void dpotrs_(const char* uplo, const int* n_, const int* nrhs_, const double* a, const int* lda_,
+                        double* b, const int* ldb_, int* info) {
+  int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  bool upper = (*uplo == 'U' || *uplo == 'u');
+  bool lower = (*uplo == 'L' || *uplo == 'l');
+  *info = 0;
+  if (!upper && !lower) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (nrhs < 0) { *info = -3; return; }
+  if (lda < max1(n)) { *info = -5; return; }
+  if (ldb < max1(n)) { *info = -7; return; }
+  if (n == 0 || nrhs == 0) return;
+  int rc = dpotrs_host(upper, n, nrhs, a, lda, b, ldb);
+  if (rc != 0) *info = rc;
+}
+
+// llacuda_<name> aliases (INTEGRATION.md option B: re-pointed blas-lapack-function-name)
+LLA_EXPORT void llacuda_dgetrf(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info) {
+  dgetrf_(m, n, a, lda, ipiv, info);
+}
+LLA_EXPORT void llacuda_dgetrs(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda,
+                               const int* ipiv, double* b, const int* ldb, int* info) {
+  dgetrs_(trans, n, nrhs, a, lda, ipiv, b, ldb, info);
+}
+LLA_EXPORT void llacuda_dgesv(const int* n, const int* nrhs, double* a, const int* lda, int* ipiv, double* b,
+                              const int* ldb, int* info) {
+  dgesv_(n, nrhs, a, lda, ipiv, b, ldb, info);
+}
+LLA_EXPORT void llacuda_dpotrf(const char* uplo, const int* n, double* a, const int* lda, int* info) {
+  dpotrf_(uplo, n, a, lda, info);
+}
+LLA_EXPORT void llacuda_dpotrs(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda,
+                               double* b, const int* ldb, int* info) {
+  dpotrs_(uplo, n, nrhs, a, lda, b, ldb, info);
+}
+
+// ------------------------------------------------------------------ device-pointer API
+LLA_EXPORT int llacuda_dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv_dev, int* info_dev) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  if (m < 0 || n < 0 || lda < max1(m)) return LLACUDA_ERR_BAD_ARG;
+  return dgetrf_dev(m, n, A, lda, ipiv_dev, info_dev, cx->stream);
+}
+LLA_EXPORT int llacuda_dgetrs_dev(char trans, int64_t n, int64_t nrhs, const double* A, int64_t lda,
+                                  const int* ipiv_dev, double* B, int64_t ldb) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  int op = opcode(trans);
+  if (op < 0 || n < 0 || nrhs < 0 || lda < max1(n) || ldb < max1(n)) return LLACUDA_ERR_BAD_ARG;
+  return dgetrs_dev(op, n, nrhs, A, lda, ipiv_dev, B, ldb, cx->stream);
+}
+LLA_EXPORT int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv_dev, double* B,
+                                 int64_t ldb, int* info_dev) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  if (n < 0 || nrhs < 0 || lda < max1(n) || ldb < max1(n)) return LLACUDA_ERR_BAD_ARG;
+  LLA_TRY(dgetrf_dev(n, n, A, lda, ipiv_dev, info_dev, cx->stream));
+  return dgetrs_dev(0, n, nrhs, A, lda, ipiv_dev, B, ldb, cx->stream, info_dev);
+}
+LLA_EXPORT int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, int* info_dev) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  bool upper = (uplo == 'U' || uplo == 'u');
+  if ((!upper && uplo != 'L' && uplo != 'l') || n < 0 || lda < max1(n)) return LLACUDA_ERR_BAD_ARG;
+  return dpotrf_dev(upper, n, A, lda, info_dev, cx->stream);
+}
+LLA_EXPORT int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const double* A, int64_t lda, double* B,
+                                  int64_t ldb) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  bool upper = (uplo == 'U' || uplo == 'u');
+  if ((!upper && uplo != 'L' && uplo != 'l') || n < 0 || nrhs < 0 || lda < max1(n) || ldb < max1(n))
+    return LLACUDA_ERR_BAD_ARG;
+  return dpotrs_dev(upper, n, nrhs, A, lda, B, ldb, cx->stream);
+}
+LLA_EXPORT int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out,
+                                      int64_t ldout) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  return dtranspose_dev(rows, cols, in, ldin, out, ldout, cx->stream);
+}

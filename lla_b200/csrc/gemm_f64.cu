@@ -111,6 +111,7 @@ struct DgemmParams {
   double* C; int64_t ldc;
   double alpha, beta;
   int tri;
+  const int* abort_flag;  // optional device flag (LAPACK INFO): non-zero => leave C untouched
 };
 
 // ---------------------------------------------------------------- the kernel
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_kernel
 
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int64_t n0 = (int64_t)blockIdx.y * BN;
+  if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
   if (p.tri == TRI_UPPER && m0 > n0 + BN - 1) return;  // tile entirely below the diagonal
   if (p.tri == TRI_LOWER && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
 
@@ -215,7 +217,9 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_kernel
 }
 
 // C = beta*C when k == 0 or alpha == 0 (netlib quick return path)
-__global__ void dscale_c_kernel(int64_t M, int64_t N, double* C, int64_t ldc, double beta, int tri) {
+__global__ void dscale_c_kernel(int64_t M, int64_t N, double* C, int64_t ldc, double beta, int tri,
+                                const int* abort_flag) {
+  if (abort_flag != nullptr && *abort_flag != 0) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t j = blockIdx.y;
   if (i >= M) return;
@@ -261,18 +265,19 @@ static inline bool aligned16(const void* p, int64_t ld) {
 }
 
 int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-              const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri, cudaStream_t st) {
+              const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri, cudaStream_t st,
+              const int* abort_flag) {
   if (m <= 0 || n <= 0) return 0;
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   if (k <= 0 || alpha == 0.0) {
     if (beta == 1.0) return 0;
     dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
-    dscale_c_kernel<<<grid, 256, 0, st>>>(m, n, C, ldc, beta, tri);
+    dscale_c_kernel<<<grid, 256, 0, st>>>(m, n, C, ldc, beta, tri, abort_flag);
     LLA_CUDA(cudaGetLastError());
     return 0;
   }
-  DgemmParams p{m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, tri};
+  DgemmParams p{m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, tri, abort_flag};
   bool al = aligned16(A, lda) && aligned16(B, ldb);
   bool ta = opa != 0, tb = opb != 0;
   // gridDim.y limit (65535) is far above any n/32 this library sees (n <= 2^21).

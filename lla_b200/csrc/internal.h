@@ -60,25 +60,28 @@ enum GemmTri { TRI_FULL = 0, TRI_UPPER = 1, TRI_LOWER = 2 };
 // op codes: 0 = N, 1 = T, 2 = C (== T for real types)
 int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha,
               const double* A, int64_t lda, const double* B, int64_t ldb,
-              double beta, double* C, int64_t ldc, int tri, cudaStream_t st);
+              double beta, double* C, int64_t ldc, int tri, cudaStream_t st,
+              const int* abort_flag = nullptr);
 int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
               const cuDoubleComplex* A, int64_t lda, const cuDoubleComplex* B, int64_t ldb,
               cuDoubleComplex beta, cuDoubleComplex* C, int64_t ldc, int tri, cudaStream_t st);
 
 // ------------------------------------------------------------------ TRSM (trsm_f64.cu), left side only
 // solves op(T) X = alpha B in place; T is m x m triangular, B is m x n
-int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n, double alpha,
-                   const double* T, int64_t ldt, double* B, int64_t ldb, cudaStream_t st);
+int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n,
+                   const double* T, int64_t ldt, double* B, int64_t ldb, cudaStream_t st,
+                   const int* abort_flag = nullptr);
 
 // ------------------------------------------------------------------ factorisations
 int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st);
+// rows i in [k1,k2) swapped with ipiv[i]-1 (1-based LAPACK pivots), forward or backward order
 int dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv,
-               bool forward, cudaStream_t st);
+               bool forward, cudaStream_t st, const int* abort_flag = nullptr);
 int dgetrs_dev(int op, int64_t n, int64_t nrhs, const double* A, int64_t lda, const int* ipiv,
-               double* B, int64_t ldb, cudaStream_t st);
+               double* B, int64_t ldb, cudaStream_t st, const int* abort_flag = nullptr);
 int dpotrf_dev(bool upper, int64_t n, double* A, int64_t lda, int* info_dev, cudaStream_t st);
 int dpotrs_dev(bool upper, int64_t n, int64_t nrhs, const double* A, int64_t lda,
-               double* B, int64_t ldb, cudaStream_t st);
+               double* B, int64_t ldb, cudaStream_t st, const int* abort_flag = nullptr);
 
 // ------------------------------------------------------------------ layout kernels (transpose.cu)
 int dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out, int64_t ldout,

@@ -1,0 +1,117 @@
+// lla_b200/csrc/trsm_f64.cu -- left-sided triangular solves op(T) X = B (in place) on the device.
+//
+// Used by GETRS / POTRS (reference call sites src/linear-algebra.lisp:269-276, :296-301) and by
+// the panel steps of the blocked LU / Cholesky factorisations.  The solve is recursive: the
+// triangle is split in two, the off-diagonal coupling is a DMMA GEMM (gemm_f64.cu), and only
+// 32 x 32 diagonal blocks are solved by substitution (column-oriented, the order of netlib xTRSM)
+// with one thread per right-hand side holding its 32 unknowns in registers.
+#include "internal.h"
+#include "../../include/llacuda.h"
+
+namespace llacuda {
+
+constexpr int TL = 32;        // leaf triangle size
+constexpr int TL_COLS = 64;   // right-hand sides per CTA
+
+// E = op(T) restricted to the leaf, identity padded, E[i][k] at e[i * 33 + k].
+// EFF_LOWER: E is lower triangular (forward substitution), else upper (backward).
+template <bool EFF_LOWER, bool TRANS, bool UNIT>
+__global__ void __launch_bounds__(TL_COLS) dtrsm_leaf_kernel(int m, int64_t n, const double* __restrict__ T,
+                                                             int64_t ldt, double* __restrict__ B, int64_t ldb,
+                                                             const int* abort_flag) {
+  if (abort_flag != nullptr && *abort_flag != 0) return;
+  __shared__ double e[TL * (TL + 1)];
+  __shared__ double bs[TL_COLS * (TL + 1)];
+  const int tid = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * TL_COLS;
+
+  for (int idx = tid; idx < TL * TL; idx += TL_COLS) {
+    int i = idx % TL, k = idx / TL;  // consecutive threads walk down a column of T
+    double v = (i == k) ? 1.0 : 0.0;
+    if (i < m && k < m && !(UNIT && i == k)) v = T[i + (int64_t)k * ldt];
+    if (TRANS) e[k * (TL + 1) + i] = v;  // E[k][i] = T[i][k]
+    else e[i * (TL + 1) + k] = v;
+  }
+  const int lane = tid & 31, w = tid >> 5;
+  for (int c = w; c < TL_COLS; c += TL_COLS / 32) {
+    int64_t gc = c0 + c;
+    double v = 0.0;
+    if (gc < n && lane < m) v = B[lane + gc * ldb];
+    bs[c * (TL + 1) + lane] = v;
+  }
+  __syncthreads();
+
+  double x[TL];
+#pragma unroll
+  for (int i = 0; i < TL; i++) x[i] = bs[tid * (TL + 1) + i];
+
+  if (EFF_LOWER) {
+#pragma unroll
+    for (int k = 0; k < TL; k++) {
+      if (!UNIT) x[k] = x[k] / e[k * (TL + 1) + k];
+#pragma unroll
+      for (int i = k + 1; i < TL; i++) x[i] = fma(-e[i * (TL + 1) + k], x[k], x[i]);
+    }
+  } else {
+#pragma unroll
+    for (int k = TL - 1; k >= 0; k--) {
+      if (!UNIT) x[k] = x[k] / e[k * (TL + 1) + k];
+#pragma unroll
+      for (int i = 0; i < k; i++) x[i] = fma(-e[i * (TL + 1) + k], x[k], x[i]);
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < TL; i++) bs[tid * (TL + 1) + i] = x[i];
+  __syncthreads();
+  for (int c = w; c < TL_COLS; c += TL_COLS / 32) {
+    int64_t gc = c0 + c;
+    if (gc < n && lane < m) B[lane + gc * ldb] = bs[c * (TL + 1) + lane];
+  }
+}
+
+static int launch_leaf(bool eff_lower, bool trans, bool unit, int m, int64_t n, const double* T, int64_t ldt,
+                       double* B, int64_t ldb, cudaStream_t st, const int* abort_flag) {
+  unsigned grid = (unsigned)((n + TL_COLS - 1) / TL_COLS);
+#define LLA_LEAF(L, TR, U) dtrsm_leaf_kernel<L, TR, U><<<grid, TL_COLS, 0, st>>>(m, n, T, ldt, B, ldb, abort_flag)
+  if (eff_lower) {
+    if (trans) { if (unit) LLA_LEAF(true, true, true); else LLA_LEAF(true, true, false); }
+    else { if (unit) LLA_LEAF(true, false, true); else LLA_LEAF(true, false, false); }
+  } else {
+    if (trans) { if (unit) LLA_LEAF(false, true, true); else LLA_LEAF(false, true, false); }
+    else { if (unit) LLA_LEAF(false, false, true); else LLA_LEAF(false, false, false); }
+  }
+#undef LLA_LEAF
+  LLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n, const double* T, int64_t ldt, double* B,
+                   int64_t ldb, cudaStream_t st, const int* abort_flag) {
+  if (m <= 0 || n <= 0) return 0;
+  const bool trans = op != 0;
+  const bool eff_lower = (upper == trans);
+  if (m <= TL) return launch_leaf(eff_lower, trans, unit, (int)m, n, T, ldt, B, ldb, st, abort_flag);
+  int64_t m1 = ((m / 2 + TL - 1) / TL) * TL;
+  int64_t m2 = m - m1;
+  const double* T11 = T;
+  const double* T22 = T + m1 + m1 * ldt;
+  const double* T21 = T + m1;        // rows m1.., cols 0..m1
+  const double* T12 = T + m1 * ldt;  // rows 0..m1, cols m1..
+  double* B1 = B;
+  double* B2 = B + m1;
+  if (eff_lower) {
+    LLA_TRY(dtrsm_left_dev(upper, op, unit, m1, n, T11, ldt, B1, ldb, st, abort_flag));
+    if (!upper) LLA_TRY(dgemm_dev(0, 0, m2, n, m1, -1.0, T21, ldt, B1, ldb, 1.0, B2, ldb, TRI_FULL, st, abort_flag));
+    else LLA_TRY(dgemm_dev(1, 0, m2, n, m1, -1.0, T12, ldt, B1, ldb, 1.0, B2, ldb, TRI_FULL, st, abort_flag));
+    LLA_TRY(dtrsm_left_dev(upper, op, unit, m2, n, T22, ldt, B2, ldb, st, abort_flag));
+  } else {
+    LLA_TRY(dtrsm_left_dev(upper, op, unit, m2, n, T22, ldt, B2, ldb, st, abort_flag));
+    if (upper) LLA_TRY(dgemm_dev(0, 0, m1, n, m2, -1.0, T12, ldt, B2, ldb, 1.0, B1, ldb, TRI_FULL, st, abort_flag));
+    else LLA_TRY(dgemm_dev(1, 0, m1, n, m2, -1.0, T21, ldt, B2, ldb, 1.0, B1, ldb, TRI_FULL, st, abort_flag));
+    LLA_TRY(dtrsm_left_dev(upper, op, unit, m1, n, T11, ldt, B1, ldb, st, abort_flag));
+  }
+  return 0;
+}
+
+}  // namespace llacuda

@@ -44,3 +44,34 @@ def probe_fp64_peak(kind, iters=20000):
     f = _sig("llacuda_probe_fp64_peak", [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)])
     _lib.check(f(kind, iters, ctypes.byref(tf), ctypes.byref(ms)), "probe")
     return tf.value, ms.value
+
+
+_ip = ctypes.c_void_p
+
+
+def dgetrf(m, n, A, lda, ipiv, info):
+    _lib.check(_sig("llacuda_dgetrf_dev", [_i64, _i64, _vp, _i64, _ip, _ip])(m, n, A, lda, ipiv, info), "dgetrf_dev")
+
+
+def dgetrs(trans, n, nrhs, A, lda, ipiv, B, ldb):
+    f = _sig("llacuda_dgetrs_dev", [_chr, _i64, _i64, _vp, _i64, _ip, _vp, _i64])
+    _lib.check(f(trans.encode(), n, nrhs, A, lda, ipiv, B, ldb), "dgetrs_dev")
+
+
+def dgesv(n, nrhs, A, lda, ipiv, B, ldb, info):
+    f = _sig("llacuda_dgesv_dev", [_i64, _i64, _vp, _i64, _ip, _vp, _i64, _ip])
+    _lib.check(f(n, nrhs, A, lda, ipiv, B, ldb, info), "dgesv_dev")
+
+
+def dpotrf(uplo, n, A, lda, info):
+    _lib.check(_sig("llacuda_dpotrf_dev", [_chr, _i64, _vp, _i64, _ip])(uplo.encode(), n, A, lda, info), "dpotrf_dev")
+
+
+def dpotrs(uplo, n, nrhs, A, lda, B, ldb):
+    f = _sig("llacuda_dpotrs_dev", [_chr, _i64, _i64, _vp, _i64, _vp, _i64])
+    _lib.check(f(uplo.encode(), n, nrhs, A, lda, B, ldb), "dpotrs_dev")
+
+
+def dtranspose(rows, cols, src, ldin, dst, ldout):
+    f = _sig("llacuda_dtranspose_dev", [_i64, _i64, _vp, _i64, _vp, _i64])
+    _lib.check(f(rows, cols, src, ldin, dst, ldout), "dtranspose_dev")

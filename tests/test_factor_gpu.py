@@ -1,0 +1,178 @@
+"""GPU parity: LU / solve / Cholesky through the Fortran drop-ins against the CPU oracle.
+
+Reference tests restated (inputs and expected values only):
+  mm-solve-lu    tests/linear-algebra.lisp:89-104
+  lu-singular    tests/linear-algebra.lisp:106-107
+  lu-random-test tests/linear-algebra.lisp:109-115
+  cholesky       tests/linear-algebra.lisp:366-385
+Bars (north_star): ipiv bit-exact with the reference LAPACK (oracle: netlib restatement AND host
+OpenBLAS); solves with scaled backward residual ||AX-B|| / (n eps ||A|| ||X||) <= 10.
+"""
+import numpy as np
+import pytest
+
+from lla_b200 import lla as L
+from oracle import lla_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+def num_eq(a, b, tol=1e-5):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b))))
+
+
+def residual(a, x, b):
+    a, x, b = np.asarray(a, dtype=np.float64), np.asarray(x), np.asarray(b)
+    n = a.shape[0]
+    return np.linalg.norm(a @ x - b) / (n * EPS * np.linalg.norm(a) * np.linalg.norm(x))
+
+
+def test_mm_solve_lu_golden():
+    a = np.array([[1, 2], [3, 4]], dtype=np.int64)
+    x = np.array([5.0, 6.0])
+    b = L.mm(a, x)
+    assert num_eq(b, [17.0, 39.0])
+    assert num_eq(L.solve(a, b), x)
+    f = L.lu(a)
+    assert list(f.ipiv_internal) == [2, 2]
+    assert num_eq(L.solve(f, b), x)
+
+
+def test_lu_singular_does_not_signal():
+    f = L.lu(np.full((2, 2), 0.5))
+    ref = O.lu(np.full((2, 2), 0.5), O.netlib())
+    assert np.array_equal(f.ipiv_internal, ref.ipiv_internal)
+    assert np.array_equal(f.lu, ref.lu)
+    with pytest.raises(L.LapackFailure) as e:
+        L.solve(np.full((2, 2), 0.5), np.ones(2))
+    assert e.value.info == 2
+
+
+def test_lu_random_reconstruction():
+    rng = np.random.default_rng(7)
+    for n in range(2, 11):
+        for _ in range(20):
+            a = rng.uniform(0, 10, (n, n))
+            f = L.lu(a)
+            ref = O.lu(a, O.netlib())
+            assert np.array_equal(f.ipiv_internal, ref.ipiv_internal)
+            p, pinv = L.ipiv(f.ipiv_internal), L.ipiv_inverse(f.ipiv_internal)
+            lu_prod = L.lu_l(f) @ L.lu_u(f)
+            assert num_eq(a[p, :], lu_prod)
+            assert num_eq(a, lu_prod[pinv, :])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 5), (33, 33), (64, 64), (100, 100), (129, 129), (300, 300),
+                                   (9, 5), (5, 9), (64, 17), (200, 70), (70, 200), (257, 130), (513, 513)])
+def test_lu_vs_oracle(shape):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    a = rng.uniform(0, 10, shape)
+    f = L.lu(a)
+    r1, r2 = O.lu(a, O.netlib()), O.lu(a, O.openblas())
+    assert np.array_equal(r1.ipiv_internal, r2.ipiv_internal)
+    assert np.array_equal(f.ipiv_internal, r1.ipiv_internal)
+    scale = max(shape) * EPS * np.abs(r1.lu).max() * 50
+    assert np.max(np.abs(f.lu - r1.lu)) <= scale
+
+
+def test_lu_ties_and_zero_columns():
+    """exact ties (first index must win), a zero column (INFO = its index, factorisation goes on)."""
+    a = np.ones((40, 40))
+    a[np.arange(40), np.arange(40)] = -1.0   # |a| all equal: pivot must always be the diagonal... after updates
+    f, r = L.lu(a), O.lu(a, O.netlib())
+    assert np.array_equal(f.ipiv_internal, r.ipiv_internal)
+    rng = np.random.default_rng(3)
+    b = rng.integers(-3, 4, (70, 70)).astype(np.float64)
+    f, r = L.lu(b), O.lu(b, O.netlib())
+    assert np.array_equal(f.ipiv_internal, r.ipiv_internal)
+    c = rng.uniform(0, 10, (50, 50))
+    c[:, 7] = 0.0
+    f, r = L.lu(c), O.lu(c, O.netlib())
+    assert np.array_equal(f.ipiv_internal, r.ipiv_internal)
+    assert np.allclose(f.lu, r.lu, atol=1e-10)
+
+
+def test_lu_nan_pivot_rule():
+    """IDAMAX skips NaN unless it is the first candidate."""
+    rng = np.random.default_rng(9)
+    a = rng.uniform(0, 10, (20, 20))
+    a[5, 0] = np.nan
+    f, r = L.lu(a), O.lu(a, O.netlib())
+    assert f.ipiv_internal[0] == r.ipiv_internal[0]
+    a = rng.uniform(0, 10, (20, 20))
+    a[0, 0] = np.nan
+    f, r = L.lu(a), O.lu(a, O.netlib())
+    assert f.ipiv_internal[0] == r.ipiv_internal[0] == 1
+
+
+@pytest.mark.parametrize("n,nrhs", [(3, 1), (37, 5), (64, 64), (130, 3), (300, 17), (512, 64)])
+def test_solve_vs_oracle(n, nrhs):
+    rng = np.random.default_rng(n + nrhs)
+    a = rng.uniform(0, 10, (n, n))
+    b = rng.uniform(0, 10, (n, nrhs)) if nrhs > 1 else rng.uniform(0, 10, n)
+    x = L.solve(a, b)
+    xr = O.solve(a, b, O.openblas())
+    assert x.shape == xr.shape == b.shape
+    assert residual(a, x, b) <= 10
+    f = L.lu(a)
+    x2 = L.solve(f, b)
+    assert residual(a, x2, b) <= 10
+    cond = np.linalg.cond(a)
+    assert np.max(np.abs(x - xr)) <= 100 * cond * EPS * np.abs(xr).max()
+
+
+def test_solve_dimension_errors():
+    with pytest.raises(L.LlaIncompatibleDimensions):
+        L.solve(np.eye(3), np.ones(4))
+    with pytest.raises(L.LlaIncompatibleDimensions):
+        L.solve(np.ones((3, 4)), np.ones(3))
+
+
+def test_cholesky_golden():
+    a = np.array([[2, -1, 0], [-1, 2, -1], [0, -1, 2]], dtype=np.float64)
+    l = np.array([[1.414214, 0, 0], [-0.7071068, 1.2247449, 0], [0.0, -0.8164966, 1.1547005]])
+    c = L.cholesky(a)
+    assert num_eq(c.left, l)
+    b = np.array([5.0, 7.0, 13.0])
+    ab = L.solve(a, b)
+    assert num_eq(L.solve(c, b), ab)
+    assert num_eq(a @ ab, b)
+    a2 = a.copy()
+    a2[0, 2] = 99.0
+    a2[0, 1] = -55.0
+    assert np.array_equal(L.cholesky(a2).left, c.left)   # only the row-major lower triangle is read
+    with pytest.raises(L.LapackFailure) as e:
+        L.cholesky(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert e.value.info == 2
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 100, 257, 600])
+def test_cholesky_vs_oracle(n):
+    rng = np.random.default_rng(n)
+    g = rng.uniform(0, 1, (n, n))
+    spd = g @ g.T + n * np.eye(n)
+    c = L.cholesky(spd)
+    r = O.cholesky(spd, O.openblas())
+    assert np.max(np.abs(c.left - r.left)) <= 20 * n * EPS * np.abs(r.left).max()
+    assert np.linalg.norm(c.left @ c.left.T - spd) / (n * EPS * np.linalg.norm(spd)) <= 10
+    nrhs = 1 + n % 7
+    b = rng.uniform(0, 1, (n, nrhs))
+    x = L.solve(c, b)
+    assert residual(spd, x, b) <= 10
+    assert np.allclose(x, O.solve_cholesky(r, b, O.openblas()), rtol=1e-9, atol=1e-12)
+
+
+def test_cholesky_not_pd_index_and_untouched_triangle():
+    rng = np.random.default_rng(2)
+    n = 150
+    g = rng.uniform(0, 1, (n, n))
+    spd = g @ g.T + n * np.eye(n)
+    bad = spd.copy()
+    bad[100, 100] = -1.0
+    with pytest.raises(L.LapackFailure) as e:
+        L.cholesky(bad)
+    with pytest.raises(O.LapackFailure) as eo:
+        O.cholesky(bad, O.netlib())
+    assert e.value.info == eo.value.info == 101
