@@ -40,6 +40,7 @@ extern "C" {
 #define LLACUDA_ERR_BAD_ARG   (-10002)
 
 /* ------------------------------------------------------------------ runtime / helpers */
+int  llacuda_set_device(int device);           /* before the first call; one device per process */
 int  llacuda_init(void);                       /* 0, or LLACUDA_ERR_NO_DEVICE (no CPU fallback) */
 const char* llacuda_last_error(void);
 int  llacuda_last_error_code(void);
@@ -49,6 +50,7 @@ void* llacuda_stream(void);                    /* cudaStream_t the *_dev calls a
 int  llacuda_set_stream(void* cuda_stream);    /* adopt a caller-owned stream (NULL = legacy default stream) */
 int  llacuda_reset_stream(void);               /* back to the library's own stream */
 int  llacuda_synchronize(void);
+unsigned long long llacuda_launch_count(void); /* llacuda kernels launched so far by this process */
 int  llacuda_last_timing(float* ms4);          /* last host-pointer call: h2d, compute, d2h, total */
 int  llacuda_malloc(void** p, size_t bytes);
 int  llacuda_free(void* p);

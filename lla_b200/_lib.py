@@ -49,5 +49,7 @@ def check(rc: int, what: str = "llacuda") -> None:
         raise LlacudaError(f"{what} failed with code {rc}: {last_error()}")
 
 
-def init() -> None:
+def init(device: int | None = None) -> None:
+    if device is not None:
+        check(lib().llacuda_set_device(int(device)), "llacuda_set_device")
     check(lib().llacuda_init(), "llacuda_init")

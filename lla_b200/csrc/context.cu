@@ -6,6 +6,7 @@
 #include "internal.h"
 #include "../../include/llacuda.h"
 
+#include <atomic>
 #include <mutex>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,9 @@ static std::mutex g_mu;
 static Context* g_ctx = nullptr;
 static thread_local char g_err[512] = "";
 static thread_local int g_err_code = 0;
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char* file, int line, const char* what, int code) {
   snprintf(g_err, sizeof(g_err), "%s:%d: %s (code %d)", file, line, what, code);
@@ -96,6 +100,20 @@ extern "C" {
 const char* llacuda_last_error(void) { return g_err; }
 int llacuda_last_error_code(void) { return g_err_code; }
 void llacuda_clear_error(void) { g_err[0] = 0; g_err_code = 0; }
+
+unsigned long long llacuda_launch_count(void) { return g_launches.load(); }
+
+int llacuda_set_device(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx && g_ctx->device != device) {
+      set_error(__FILE__, __LINE__, "llacuda_set_device: context already bound to another device", g_ctx->device);
+      return LLACUDA_ERR_BAD_ARG;
+    }
+  }
+  LLA_CUDA(cudaSetDevice(device));
+  return 0;
+}
 
 int llacuda_init(void) { return ctx() ? 0 : LLACUDA_ERR_NO_DEVICE; }
 

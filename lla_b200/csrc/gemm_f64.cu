@@ -19,6 +19,8 @@
 #include "internal.h"
 #include "../../include/llacuda.h"
 
+#include <cstdlib>
+
 namespace llacuda {
 
 // ---------------------------------------------------------------- PTX helpers
@@ -119,7 +121,7 @@ struct DgemmParams {
 // Fragment ownership (PTX ISA, mma.m8n8k4.f64): lane l holds A[l/4][l%4], B[l%4][l/4],
 // C[l/4][2*(l%4) + {0,1}].
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, bool AL16, int MINB>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_kernel(DgemmParams p) {
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) lla_dgemm_kernel(DgemmParams p) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr bool A_MN = !TA;  // op(A)[m][k] = A[m + k*lda] when not transposed
   constexpr bool B_MN = TB;   // op(B)[k][n] = B[n + k*ldb] when transposed
@@ -130,8 +132,18 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_kernel
 
   extern __shared__ __align__(16) double smem[];
 
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int64_t n0 = (int64_t)blockIdx.y * BN;
+  // grouped rasterisation: consecutive CTAs walk GROUP_M row-tiles of one column-tile strip, so the
+  // CTAs resident at any time cover a compact block of C and share their A / B panels through L2
+  constexpr int GROUP_M = 16;
+  const int tiles_m = (int)((p.M + BM - 1) / BM), tiles_n = (int)((p.N + BN - 1) / BN);
+  const int pid = blockIdx.x;
+  const int group = pid / (GROUP_M * tiles_n);
+  const int first_m = group * GROUP_M;
+  const int gsz = (tiles_m - first_m) < GROUP_M ? (tiles_m - first_m) : GROUP_M;
+  const int tm = first_m + (pid % (GROUP_M * tiles_n)) % gsz;
+  const int tn = (pid % (GROUP_M * tiles_n)) / gsz;
+  const int64_t m0 = (int64_t)tm * BM;
+  const int64_t n0 = (int64_t)tn * BN;
   if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
   if (p.tri == TRI_UPPER && m0 > n0 + BN - 1) return;  // tile entirely below the diagonal
   if (p.tri == TRI_LOWER && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_kernel
 }
 
 // C = beta*C when k == 0 or alpha == 0 (netlib quick return path)
-__global__ void dscale_c_kernel(int64_t M, int64_t N, double* C, int64_t ldc, double beta, int tri,
+__global__ void lla_dscale_c_kernel(int64_t M, int64_t N, double* C, int64_t ldc, double beta, int tri,
                                 const int* abort_flag) {
   if (abort_flag != nullptr && *abort_flag != 0) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,14 +247,16 @@ static int launch_cfg(const DgemmParams& p, cudaStream_t st) {
   using TSA = TileShape<BM, BK, !TA>;
   using TSB = TileShape<BN, BK, TB>;
   constexpr size_t SMEM = size_t(STAGES) * (TSA::ELEMS + TSB::ELEMS) * sizeof(double);
-  auto kern = dgemm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB, AL16, MINB>;
+  auto kern = lla_dgemm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB, AL16, MINB>;
   static bool configured = false;
   if (!configured) {
     LLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
+  int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  dim3 grid((unsigned)tiles);
   kern<<<grid, NT, SMEM, st>>>(p);
+  count_launch();
   LLA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -251,8 +265,14 @@ template <bool TA, bool TB, bool AL16>
 static int launch_shape(const DgemmParams& p, cudaStream_t st, int sm_count) {
   int64_t big_tiles = ((p.M + 127) / 128) * ((p.N + 127) / 128);
   if (p.tri != TRI_FULL) big_tiles = big_tiles / 2 + 1;
-  if (big_tiles >= 2 * (int64_t)sm_count)
+  if (big_tiles >= 2 * (int64_t)sm_count) {
+    static int cfg = -1;
+    if (cfg < 0) { const char* e = getenv("LLACUDA_GEMM_CFG"); cfg = e ? atoi(e) : 0; }
+    if (cfg == 1) return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
+    if (cfg == 2) return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st);
+    if (cfg == 3) return launch_cfg<64, 128, 16, 32, 64, 4, TA, TB, AL16, 2>(p, st);
     return launch_cfg<128, 128, 16, 64, 32, 4, TA, TB, AL16, 1>(p, st);
+  }
   if (p.N <= 32 || p.M <= 32) {
     if (p.N <= 32) return launch_cfg<128, 32, 16, 32, 32, 4, TA, TB, AL16, 2>(p, st);
     return launch_cfg<32, 128, 16, 32, 32, 4, TA, TB, AL16, 2>(p, st);
@@ -273,7 +293,8 @@ int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha, c
   if (k <= 0 || alpha == 0.0) {
     if (beta == 1.0) return 0;
     dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
-    dscale_c_kernel<<<grid, 256, 0, st>>>(m, n, C, ldc, beta, tri, abort_flag);
+    lla_dscale_c_kernel<<<grid, 256, 0, st>>>(m, n, C, ldc, beta, tri, abort_flag);
+    count_launch();
     LLA_CUDA(cudaGetLastError());
     return 0;
   }

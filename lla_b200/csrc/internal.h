@@ -47,6 +47,9 @@ struct Context {
 Context* ctx();                       // lazily initialised, per process, current device
 int ensure_workspace(size_t bytes);   // ctx()->ws valid for >= bytes afterwards
 
+// number of llacuda kernels launched by this process (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+
 // device scratch allocations that live for one call
 struct DevBuf {
   void* p = nullptr;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* count, unsigned target) {
 
 // A: top-left of the panel (diagonal element of the full matrix), m rows x w columns.
 // ipiv/info are indexed / valued relative to the full matrix through `off` (global row of the top).
-__global__ void __launch_bounds__(PR) dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
+__global__ void __launch_bounds__(PR) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
                                                           int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
                                                           PanelSlot* __restrict__ slots, PanelShared* __restrict__ shared_rows,
                                                           unsigned* __restrict__ bar) {
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(PR) dgetf2_panel_kernel(double* __restrict__ A
 constexpr int SW_CHUNK = 32;
 constexpr int SW_COLS = 16;
 
-__global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) dlaswp_kernel(double* __restrict__ A, int64_t lda, int64_t ncols,
+__global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) lla_dlaswp_kernel(double* __restrict__ A, int64_t lda, int64_t ncols,
                                                                        int64_t skip0, int64_t skip1, int64_t k1, int64_t k2,
                                                                        const int* __restrict__ ipiv, bool forward,
                                                                        const int* abort_flag) {
@@ -264,7 +264,8 @@ int dlaswp_skip_dev(int64_t ncols, int64_t skip0, int64_t skip1, double* A, int6
   int64_t eff = ncols - (skip1 - skip0);
   if (eff <= 0 || k2 <= k1) return 0;
   unsigned grid = (unsigned)((eff + SW_COLS - 1) / SW_COLS);
-  dlaswp_kernel<<<grid, 2 * SW_CHUNK * SW_COLS, 0, st>>>(A, lda, ncols, skip0, skip1, k1, k2, ipiv, forward, abort_flag);
+  lla_dlaswp_kernel<<<grid, 2 * SW_CHUNK * SW_COLS, 0, st>>>(A, lda, ncols, skip0, skip1, k1, k2, ipiv, forward, abort_flag);
+  count_launch();
   LLA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -299,7 +300,8 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   PanelShared* sr_ = L.shared_rows;
   unsigned* bar_ = L.bar;
   void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &slots_, &sr_, &bar_};
-  LLA_CUDA(cudaLaunchCooperativeKernel((void*)dgetf2_panel_kernel, dim3(G), dim3(PR), args, 0, L.st));
+  LLA_CUDA(cudaLaunchCooperativeKernel((void*)lla_dgetf2_panel_kernel, dim3(G), dim3(PR), args, 0, L.st));
+  count_launch();
   // interchange the rest of the rows now: columns [0, j0) and [j0+w, N)
   int64_t npiv = m < w ? m : w;
   LLA_TRY(dlaswp_skip_dev(L.N, j0, j0 + w, L.A, L.lda, j0, j0 + npiv, L.ipiv, true, L.st, nullptr));
@@ -327,7 +329,7 @@ static int lu_rec(const LuCtx& L, int64_t j0, int64_t m, int64_t n) {
   return 0;
 }
 
-__global__ void iota_ipiv_kernel(int* ipiv, int64_t n) {
+__global__ void lla_iota_ipiv_kernel(int* ipiv, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ipiv[i] = (int)(i + 1);
 }
@@ -340,7 +342,7 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   int maxG = (int)((m + PR - 1) / PR);
   // co-residency bound of the cooperative panel kernel
   int per_sm = 0;
-  LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dgetf2_panel_kernel, PR, 0));
+  LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel, PR, 0));
   if ((int64_t)per_sm * c->sm_count < maxG) {
     set_error(__FILE__, __LINE__, "dgetrf: panel too tall for one cooperative launch", (int)m);
     return LLACUDA_ERR_BAD_ARG;

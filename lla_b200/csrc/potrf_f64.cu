@@ -17,7 +17,7 @@ namespace llacuda {
 constexpr int CL = 32;  // leaf size
 
 // one CTA of 32x32 threads factors the upper triangle of an n x n (n <= 32) block
-__global__ void __launch_bounds__(CL * CL) dpotf2_leaf_kernel(int n, double* __restrict__ A, int64_t lda, int off,
+__global__ void __launch_bounds__(CL * CL) lla_dpotf2_leaf_kernel(int n, double* __restrict__ A, int64_t lda, int off,
                                                               int* __restrict__ info) {
   if (*info != 0) return;
   __shared__ double s[CL][CL + 1];
@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(CL * CL) dpotf2_leaf_kernel(int n, double* __r
 static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, int* info, cudaStream_t st) {
   if (n <= 0) return 0;
   if (n <= CL) {
-    dpotf2_leaf_kernel<<<1, dim3(CL, CL), 0, st>>>((int)n, A, lda, (int)off, info);
+    lla_dpotf2_leaf_kernel<<<1, dim3(CL, CL), 0, st>>>((int)n, A, lda, (int)off, info);
+    count_launch();
     LLA_CUDA(cudaGetLastError());
     return 0;
   }

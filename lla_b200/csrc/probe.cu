@@ -9,7 +9,7 @@
 namespace llacuda {
 
 template <int CHAINS>
-__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters) {
+__global__ void __launch_bounds__(256) lla_dmma_probe_kernel(double* out, int iters) {
   double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
   double c[CHAINS][2];
 #pragma unroll
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters)
 }
 
 template <int CHAINS>
-__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters) {
+__global__ void __launch_bounds__(256) lla_dfma_probe_kernel(double* out, int iters) {
   double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * threadIdx.x;
   double c[CHAINS];
 #pragma unroll
@@ -59,8 +59,9 @@ extern "C" int llacuda_probe_fp64_peak(int kind, int iters, double* tflops, floa
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {
     LLA_CUDA(cudaEventRecord(e0, c->stream));
-    if (kind == 0) dmma_probe_kernel<CH><<<grid, 256, 0, c->stream>>>((double*)out.p, iters);
-    else dfma_probe_kernel<CH><<<grid, 256, 0, c->stream>>>((double*)out.p, iters);
+    if (kind == 0) lla_dmma_probe_kernel<CH><<<grid, 256, 0, c->stream>>>((double*)out.p, iters);
+    else lla_dfma_probe_kernel<CH><<<grid, 256, 0, c->stream>>>((double*)out.p, iters);
+    count_launch();
     LLA_CUDA(cudaGetLastError());
     LLA_CUDA(cudaEventRecord(e1, c->stream));
     LLA_CUDA(cudaEventSynchronize(e1));

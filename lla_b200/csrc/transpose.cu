@@ -10,7 +10,7 @@ namespace llacuda {
 constexpr int TT = 32;
 
 // out[c + r*ldout] = in[r + c*ldin],  in: rows x cols column-major
-__global__ void __launch_bounds__(TT * 8) dtranspose_kernel(int64_t rows, int64_t cols, const double* __restrict__ in,
+__global__ void __launch_bounds__(TT * 8) lla_dtranspose_kernel(int64_t rows, int64_t cols, const double* __restrict__ in,
                                                             int64_t ldin, double* __restrict__ out, int64_t ldout) {
   __shared__ double t[TT][TT + 1];
   const int64_t r0 = (int64_t)blockIdx.x * TT, c0 = (int64_t)blockIdx.y * TT;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(TT * 8) dtranspose_kernel(int64_t rows, int64_
 }
 
 // A <- A^T for a square n x n matrix; each CTA swaps one tile pair (diagonal tiles transpose in place)
-__global__ void __launch_bounds__(TT * 8) dtranspose_inplace_kernel(int64_t n, double* __restrict__ A, int64_t lda) {
+__global__ void __launch_bounds__(TT * 8) lla_dtranspose_inplace_kernel(int64_t n, double* __restrict__ A, int64_t lda) {
   const int64_t bi = blockIdx.x, bj = blockIdx.y;
   if (bi > bj) return;
   __shared__ double t1[TT][TT + 1];
@@ -57,7 +57,8 @@ int dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, d
                    cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return 0;
   dim3 grid((unsigned)((rows + TT - 1) / TT), (unsigned)((cols + TT - 1) / TT));
-  dtranspose_kernel<<<grid, dim3(TT, 8), 0, st>>>(rows, cols, in, ldin, out, ldout);
+  lla_dtranspose_kernel<<<grid, dim3(TT, 8), 0, st>>>(rows, cols, in, ldin, out, ldout);
+  count_launch();
   LLA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -65,7 +66,8 @@ int dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, d
 int dtranspose_inplace_dev(int64_t n, double* A, int64_t lda, cudaStream_t st) {
   if (n <= 1) return 0;
   unsigned g = (unsigned)((n + TT - 1) / TT);
-  dtranspose_inplace_kernel<<<dim3(g, g), dim3(TT, 8), 0, st>>>(n, A, lda);
+  lla_dtranspose_inplace_kernel<<<dim3(g, g), dim3(TT, 8), 0, st>>>(n, A, lda);
+  count_launch();
   LLA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -16,7 +16,7 @@ constexpr int TL_COLS = 64;   // right-hand sides per CTA
 // E = op(T) restricted to the leaf, identity padded, E[i][k] at e[i * 33 + k].
 // EFF_LOWER: E is lower triangular (forward substitution), else upper (backward).
 template <bool EFF_LOWER, bool TRANS, bool UNIT>
-__global__ void __launch_bounds__(TL_COLS) dtrsm_leaf_kernel(int m, int64_t n, const double* __restrict__ T,
+__global__ void __launch_bounds__(TL_COLS) lla_dtrsm_leaf_kernel(int m, int64_t n, const double* __restrict__ T,
                                                              int64_t ldt, double* __restrict__ B, int64_t ldb,
                                                              const int* abort_flag) {
   if (abort_flag != nullptr && *abort_flag != 0) return;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TL_COLS) dtrsm_leaf_kernel(int m, int64_t n, c
 static int launch_leaf(bool eff_lower, bool trans, bool unit, int m, int64_t n, const double* T, int64_t ldt,
                        double* B, int64_t ldb, cudaStream_t st, const int* abort_flag) {
   unsigned grid = (unsigned)((n + TL_COLS - 1) / TL_COLS);
-#define LLA_LEAF(L, TR, U) dtrsm_leaf_kernel<L, TR, U><<<grid, TL_COLS, 0, st>>>(m, n, T, ldt, B, ldb, abort_flag)
+#define LLA_LEAF(L, TR, U) lla_dtrsm_leaf_kernel<L, TR, U><<<grid, TL_COLS, 0, st>>>(m, n, T, ldt, B, ldb, abort_flag)
   if (eff_lower) {
     if (trans) { if (unit) LLA_LEAF(true, true, true); else LLA_LEAF(true, true, false); }
     else { if (unit) LLA_LEAF(true, false, true); else LLA_LEAF(true, false, false); }
@@ -82,6 +82,7 @@ static int launch_leaf(bool eff_lower, bool trans, bool unit, int m, int64_t n, 
     else { if (unit) LLA_LEAF(false, false, true); else LLA_LEAF(false, false, false); }
   }
 #undef LLA_LEAF
+  count_launch();
   LLA_CUDA(cudaGetLastError());
   return 0;
 }
