@@ -78,8 +78,23 @@ int ensure_workspace(size_t bytes) {
   }
   size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes;
   LLA_CUDA(cudaMalloc(&c->ws, want));
+  LLA_CUDA(cudaMemset(c->ws, 0, want));  // the panel exchange area must not start with stray tags
   c->ws_bytes = want;
   return 0;
+}
+
+int Arena::reserve(size_t bytes) {
+  LLA_TRY(ensure_workspace(bytes + 4096));
+  base = (char*)ctx()->ws;
+  cap = ctx()->ws_bytes;
+  used = 0;
+  return 0;
+}
+void* Arena::take(size_t bytes) {
+  size_t a = (used + 255) & ~size_t(255);
+  if (a + bytes > cap) return nullptr;
+  used = a + bytes;
+  return base + a;
 }
 
 int DevBuf::alloc(size_t n) {

@@ -262,16 +262,21 @@ static int launch_cfg(const DgemmParams& p, cudaStream_t st) {
 }
 
 template <bool TA, bool TB, bool AL16>
-static int launch_shape(const DgemmParams& p, cudaStream_t st, int sm_count) {
+static int launch_shape(const DgemmParams& p, cudaStream_t st, int sm_count, int hint) {
+  if (hint == GEMM_INPLACE_B) return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
   int64_t big_tiles = ((p.M + 127) / 128) * ((p.N + 127) / 128);
   if (p.tri != TRI_FULL) big_tiles = big_tiles / 2 + 1;
   if (big_tiles >= 2 * (int64_t)sm_count) {
+    // measured on B200 (profiles/r01_gemm_config_sweep.txt): two 128x64 CTAs per SM hide each
+    // other's barrier bubbles (33.6 vs 31.5 TFLOP/s) unless op(A) is K-contiguous, where the
+    // 128x128 tile with BK = 32 is the faster one (32.2 vs 25.9 TFLOP/s).
     static int cfg = -1;
-    if (cfg < 0) { const char* e = getenv("LLACUDA_GEMM_CFG"); cfg = e ? atoi(e) : 0; }
+    if (cfg < 0) { const char* e = getenv("LLACUDA_GEMM_CFG"); cfg = e ? atoi(e) : 9; }
+    if (cfg == 0) return launch_cfg<128, 128, 16, 64, 32, 4, TA, TB, AL16, 1>(p, st);
     if (cfg == 1) return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
     if (cfg == 2) return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st);
-    if (cfg == 3) return launch_cfg<64, 128, 16, 32, 64, 4, TA, TB, AL16, 2>(p, st);
-    return launch_cfg<128, 128, 16, 64, 32, 4, TA, TB, AL16, 1>(p, st);
+    if (TA) return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st);
+    return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
   }
   if (p.N <= 32 || p.M <= 32) {
     if (p.N <= 32) return launch_cfg<128, 32, 16, 32, 32, 4, TA, TB, AL16, 2>(p, st);
@@ -286,7 +291,7 @@ static inline bool aligned16(const void* p, int64_t ld) {
 
 int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
               const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri, cudaStream_t st,
-              const int* abort_flag) {
+              const int* abort_flag, int hint) {
   if (m <= 0 || n <= 0) return 0;
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
@@ -303,7 +308,7 @@ int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha, c
   bool ta = opa != 0, tb = opb != 0;
   // gridDim.y limit (65535) is far above any n/32 this library sees (n <= 2^21).
 #define LLA_DISPATCH(TA_, TB_)                                             \
-  (al ? launch_shape<TA_, TB_, true>(p, st, c->sm_count) : launch_shape<TA_, TB_, false>(p, st, c->sm_count))
+  (al ? launch_shape<TA_, TB_, true>(p, st, c->sm_count, hint) : launch_shape<TA_, TB_, false>(p, st, c->sm_count, hint))
   if (!ta && !tb) return LLA_DISPATCH(false, false);
   if (ta && !tb) return LLA_DISPATCH(true, false);
   if (!ta && tb) return LLA_DISPATCH(false, true);

@@ -47,6 +47,15 @@ struct Context {
 Context* ctx();                       // lazily initialised, per process, current device
 int ensure_workspace(size_t bytes);   // ctx()->ws valid for >= bytes afterwards
 
+// Bump allocator over ctx()->ws for the scratch of ONE top-level call: reserve() once with the
+// total (may grow the arena: synchronises), then take() pieces (256-byte aligned).
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  int reserve(size_t bytes);
+  void* take(size_t bytes);
+};
+
 // number of llacuda kernels launched by this process (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 
@@ -64,7 +73,10 @@ enum GemmTri { TRI_FULL = 0, TRI_UPPER = 1, TRI_LOWER = 2 };
 int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha,
               const double* A, int64_t lda, const double* B, int64_t ldb,
               double beta, double* C, int64_t ldc, int tri, cudaStream_t st,
-              const int* abort_flag = nullptr);
+              const int* abort_flag = nullptr, int hint = 0);
+// hint 1: m <= 128 and C aliases B (in-place product): force a single row of 128-row tiles so
+// that every column slab of B/C is read and then written by exactly one CTA.
+enum GemmHint { GEMM_AUTO = 0, GEMM_INPLACE_B = 1 };
 int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
               const cuDoubleComplex* A, int64_t lda, const cuDoubleComplex* B, int64_t ldb,
               cuDoubleComplex beta, cuDoubleComplex* C, int64_t ldc, int tri, cudaStream_t st);
@@ -74,6 +86,16 @@ int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex
 int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n,
                    const double* T, int64_t ldt, double* B, int64_t ldb, cudaStream_t st,
                    const int* abort_flag = nullptr);
+
+// inverse-based solve: Tinv holds the inverses of the IB x IB diagonal blocks of T (block b at
+// Tinv + b*IB*IB, leading dimension IB), produced by dtrtri_blocks_dev or by the factorisations
+constexpr int IB = 128;
+int dtrtri_blocks_dev(bool upper, bool unit, int64_t m, const double* T, int64_t ldt, double* Tinv,
+                      cudaStream_t st, const int* abort_flag = nullptr);
+int dtrsm_left_inv_dev(bool upper, int op, int64_t m, int64_t n, const double* T, int64_t ldt,
+                       const double* Tinv, double* B, int64_t ldb, cudaStream_t st,
+                       const int* abort_flag = nullptr);
+inline size_t tinv_bytes(int64_t m) { return (size_t)((m + IB - 1) / IB) * IB * IB * sizeof(double); }
 
 // ------------------------------------------------------------------ factorisations
 int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st);

@@ -26,161 +26,174 @@
 namespace llacuda {
 
 constexpr int PW = 32;     // leaf panel width (columns held in registers per row)
-constexpr int PR = 128;    // rows (= threads) per CTA
+constexpr int PR = 256;    // rows (= threads) per CTA
 
-struct PanelSlot {        // one per CTA per parity
-  double absval;          // candidate |a|, -1 if the CTA has no candidate
-  int row;                // candidate row, relative to the panel top
-  int pad;
-  double vals[PW];        // the candidate row
-};
+// Cross-CTA exchange uses self-validating 8-byte words (32 bits of payload + a 32-bit tag, the
+// NCCL "LL" idea): an aligned 8-byte store is single-copy atomic, so a reader that sees the
+// expected tag in every word holds a consistent record and no fence or atomic is on the critical
+// path.  tag = (launch epoch << 6) | (column + 1) is unique per launch and column.
+struct __align__(16) LLDouble { unsigned lo, tag0, hi, tag1; };
+struct __align__(32) PanelHdr { LLDouble absval; unsigned row, tag2, pad, tag3; };
+struct PanelRow { LLDouble v[PW]; };
 
-struct PanelShared {      // published by the owner of row j
-  double rowj[PW];
-};
-
-// monotone grid barrier: `count` starts at 0 for every launch
-__device__ __forceinline__ void grid_barrier(unsigned* count, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(count, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(count) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
+__device__ __forceinline__ void ll_store(LLDouble* p, double x, unsigned tag) {
+  unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
+__device__ __forceinline__ bool ll_load(const LLDouble* p, unsigned tag, double& x) {
+  unsigned a, b, c, d;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  x = __hiloint2double((int)c, (int)a);
+  return b == tag && d == tag;
+}
+
+constexpr int PPITCH = PR + 1;                       // shared-memory pitch of one panel column
+constexpr size_t PANEL_SMEM = (size_t)PW * PPITCH * sizeof(double);
 
 // A: top-left of the panel (diagonal element of the full matrix), m rows x w columns.
 // ipiv/info are indexed / valued relative to the full matrix through `off` (global row of the top).
-__global__ void __launch_bounds__(PR) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
-                                                          int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
-                                                          PanelSlot* __restrict__ slots, PanelShared* __restrict__ shared_rows,
-                                                          unsigned* __restrict__ bar) {
+// The CTA's 256 x 32 slice of the panel lives in shared memory (column c at S + c*PPITCH), thread t
+// owns row t; warp 0 runs the cross-CTA exchange of every column.  These kernels are bound by
+// instruction latency (a handful of warps per SM), so the per-column instruction count is what
+// is being minimised here -- no unrolled register-array selects, real loops with dynamic bounds.
+__global__ void __launch_bounds__(PR, 2) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
+                                                                 int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
+                                                                 PanelHdr* __restrict__ hdrs, PanelRow* __restrict__ rows,
+                                                                 PanelRow* __restrict__ rowj, unsigned epoch) {
+  extern __shared__ __align__(16) double S[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
-  const int64_t row = (int64_t)blockIdx.x * PR + tid;  // relative to the panel top
-  const bool live = row < m;
+  const int64_t row0 = (int64_t)blockIdx.x * PR;
+  const int64_t grow = row0 + tid;  // relative to the panel top
+  const bool live = grow < m;
   const int nsteps = (int)(m < w ? m : w);
 
-  double a[PW];
+  {
+    double v[PW];
 #pragma unroll
-  for (int c = 0; c < PW; c++) a[c] = (live && c < w) ? A[row + (int64_t)c * lda] : 0.0;
+    for (int c = 0; c < PW; c++) v[c] = (live && c < w) ? A[grow + (int64_t)c * lda] : 0.0;
+#pragma unroll
+    for (int c = 0; c < PW; c++) S[c * PPITCH + tid] = v[c];
+  }
 
   __shared__ double s_val[PR / 32];
   __shared__ int s_row[PR / 32];
   __shared__ double s_prow[PW];
   __shared__ double s_rowj[PW];
   __shared__ int s_piv;
+  __syncthreads();
 
   const double sfmin = DBL_MIN;
 
+#pragma unroll 1
+  for (int j = 0; j < nsteps; j++) {
+    const int par = j & 1;
+    const unsigned tag = (epoch << 6) | (unsigned)(j + 1);
+    // ---- 1. candidate of this warp: first row (>= j) with the largest |a[j]|; NaN only wins as row j
+    double v = -1.0;
+    int r = 0x7fffffff;
+    if (live && grow >= j) {
+      double x = fabs(S[j * PPITCH + tid]);
+      bool isn = (x != x);
+      if (grow == j && isn) v = INFINITY;  // IDAMAX: dmax = NaN, nothing compares greater
+      else v = isn ? -1.0 : x;
+      r = (int)grow;
+    }
 #pragma unroll
-  for (int j = 0; j < PW; j++) {
-    if (j < nsteps) {
-      const int par = j & 1;
-      // ---- 1. local candidate: first row (>= j) with the largest |a[j]|; NaN only wins as row j
-      double v = -1.0;
-      int r = 0x7fffffff;
-      if (live && row >= j) {
-        double x = fabs(a[j]);
-        bool isn = (x != x);
-        if (row == j && isn) v = INFINITY;  // IDAMAX: dmax = NaN, nothing compares greater
-        else v = isn ? -1.0 : x;
-        r = (int)row;
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      int orow = __shfl_xor_sync(0xffffffffu, r, o);
+      if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+    }
+    if (lane == 0) { s_val[warp] = v; s_row[warp] = r; }
+    __syncthreads();
+    // ---- 2. warp 0: CTA candidate, publish, wait for every CTA, pick the winner, fetch its row
+    if (warp == 0) {
+      double bv = (lane < PR / 32) ? s_val[lane] : -3.0;
+      int br = (lane < PR / 32) ? s_row[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = PR / 64; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int orow = __shfl_xor_sync(0xffffffffu, br, o);
+        if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
+      }
+      bv = __shfl_sync(0xffffffffu, bv, 0);
+      br = __shfl_sync(0xffffffffu, br, 0);
+      const int lr = br - (int)row0;  // the CTA's candidate row is always one of its own live rows
+      ll_store(&rows[par * G + blockIdx.x].v[lane], S[lane * PPITCH + lr], tag);
+      if (blockIdx.x == 0) ll_store(&rowj[par].v[lane], S[lane * PPITCH + j], tag);  // row j lives in CTA 0
+      if (lane == 0) {
+        PanelHdr* h = &hdrs[par * G + blockIdx.x];
+        ll_store(&h->absval, bv, tag);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(&h->row), "r"((unsigned)br), "r"(tag),
+                     "r"(0u), "r"(tag) : "memory");
+      }
+      double wv = -2.0;
+      int wr = 0x7fffffff, wslot = 0;
+      for (int q = lane; q < G; q += 32) {
+        const PanelHdr* h = &hdrs[par * G + q];
+        double sv;
+        unsigned r0, t0, r1 = 0, t1;
+        bool ok;
+        do {
+          ok = ll_load(&h->absval, tag, sv);
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(t0), "=r"(r1), "=r"(t1) : "l"(&h->row) : "memory");
+          ok = ok && t0 == tag && t1 == tag;
+        } while (!ok);
+        int sr = (int)r0;
+        if (sv > wv || (sv == wv && sr < wr)) { wv = sv; wr = sr; wslot = q; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int orow = __shfl_xor_sync(0xffffffffu, r, o);
-        if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+        double ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        int orow = __shfl_xor_sync(0xffffffffu, wr, o);
+        int oslot = __shfl_xor_sync(0xffffffffu, wslot, o);
+        if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wslot = oslot; }
       }
-      if (lane == 0) { s_val[warp] = v; s_row[warp] = r; }
-      __syncthreads();
-      if (tid == 0) {
-        double bv = s_val[0];
-        int br = s_row[0];
-#pragma unroll
-        for (int q = 1; q < PR / 32; q++)
-          if (s_val[q] > bv || (s_val[q] == bv && s_row[q] < br)) { bv = s_val[q]; br = s_row[q]; }
-        s_piv = br;
-        slots[par * G + blockIdx.x].absval = bv;
-        slots[par * G + blockIdx.x].row = br;
-      }
-      __syncthreads();
-      // the thread that owns the CTA's candidate row publishes it; the owner of row j publishes row j
-      if (live && (int)row == s_piv) {
-        double* dst = slots[par * G + blockIdx.x].vals;
-#pragma unroll
-        for (int c = 0; c < PW; c++) dst[c] = a[c];
-      }
-      if (live && row == j) {
-        double* dst = shared_rows[par].rowj;
-#pragma unroll
-        for (int c = 0; c < PW; c++) dst[c] = a[c];
-      }
-      // ---- 2. the one grid-wide barrier of this column
-      grid_barrier(bar, (unsigned)G * (unsigned)(j + 1));
-      // ---- 3. every CTA picks the same winner
-      if (warp == 0) {
-        double bv = -2.0;
-        int br = 0x7fffffff, bslot = 0;
-        for (int q = lane; q < G; q += 32) {
-          const PanelSlot* s = &slots[par * G + q];
-          double sv = __ldcg(&s->absval);
-          int sr = __ldcg(&s->row);
-          if (sv > bv || (sv == bv && sr < br)) { bv = sv; br = sr; bslot = q; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          int orow = __shfl_xor_sync(0xffffffffu, br, o);
-          int oslot = __shfl_xor_sync(0xffffffffu, bslot, o);
-          if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; bslot = oslot; }
-        }
-        s_prow[lane] = __ldcg(&slots[par * G + bslot].vals[lane]);
-        s_rowj[lane] = __ldcg(&shared_rows[par].rowj[lane]);
-        if (lane == 0) s_piv = br;
-      }
-      __syncthreads();
-      const int p = s_piv;
-      const double piv = s_prow[j];
-      if (blockIdx.x == 0 && tid == 0) {
-        ipiv[off + j] = (int)(off + p + 1);
-        if (piv == 0.0 && *info == 0) *info = (int)(off + j + 1);
-      }
-      // ---- 4. swap (only when the pivot is non-zero, as DGETF2 does), scale, rank-1 update
-      if (piv != 0.0) {
-        if (p != j) {
-          if (live && row == j) {
-#pragma unroll
-            for (int c = 0; c < PW; c++) a[c] = s_prow[c];
-          } else if (live && (int)row == p) {
-#pragma unroll
-            for (int c = 0; c < PW; c++) a[c] = s_rowj[c];
-          }
-        }
-        if (live && row > j) {
-          if (fabs(piv) >= sfmin) a[j] = a[j] * (1.0 / piv);
-          else a[j] = a[j] / piv;
-        }
-      }
-      if (live && row > j) {
-        const double l = a[j];
-        // s_prow is row j of the panel after the interchange (a zero pivot implies p == j)
-#pragma unroll
-        for (int c = j + 1; c < PW; c++) a[c] = fma(-l, s_prow[c], a[c]);
-      }
-      __syncthreads();  // s_prow / s_rowj / s_piv are rewritten in the next column
+      double pv, rj;
+      while (!ll_load(&rows[par * G + wslot].v[lane], tag, pv)) {}
+      while (!ll_load(&rowj[par].v[lane], tag, rj)) {}
+      s_prow[lane] = pv;
+      s_rowj[lane] = rj;
+      if (lane == 0) s_piv = wr;
     }
+    __syncthreads();
+    const int p = s_piv;
+    const double piv = s_prow[j];
+    if (blockIdx.x == 0 && tid == 0) {
+      ipiv[off + j] = (int)(off + p + 1);
+      if (piv == 0.0 && *info == 0) *info = (int)(off + j + 1);
+    }
+    // ---- 3. swap (only when the pivot is non-zero, as DGETF2 does), scale, rank-1 update
+    const bool swapped = (piv != 0.0) && (p != j);
+    if (live && grow == j) {
+      if (swapped)
+        for (int c = 0; c < PW; c++) S[c * PPITCH + tid] = s_prow[c];
+    } else if (live && grow > j) {
+      const bool isp = swapped && ((int)grow == p);  // this row receives the old row j
+      if (isp)
+        for (int c = 0; c < j; c++) S[c * PPITCH + tid] = s_rowj[c];
+      const double aj = isp ? s_rowj[j] : S[j * PPITCH + tid];
+      double l = aj;
+      if (piv != 0.0) l = (fabs(piv) >= sfmin) ? aj * (1.0 / piv) : aj / piv;
+      S[j * PPITCH + tid] = l;
+      // s_prow is row j of the panel after the interchange (a zero pivot implies p == j)
+      if (isp) {
+        for (int c = j + 1; c < PW; c++) S[c * PPITCH + tid] = fma(-l, s_prow[c], s_rowj[c]);
+      } else {
+#pragma unroll 4
+        for (int c = j + 1; c < PW; c++) S[c * PPITCH + tid] = fma(-l, s_prow[c], S[c * PPITCH + tid]);
+      }
+    }
+    __syncthreads();  // s_prow / s_rowj / s_piv / s_val are rewritten in the next column
   }
 
+  if (live) {
 #pragma unroll
-  for (int c = 0; c < PW; c++)
-    if (live && c < w) A[row + (int64_t)c * lda] = a[c];
+    for (int c = 0; c < PW; c++)
+      if (c < w) A[grow + (int64_t)c * lda] = S[c * PPITCH + tid];
+  }
 }
 
 // ------------------------------------------------------------------ row interchanges
@@ -281,57 +294,136 @@ struct LuCtx {
   int64_t lda, M, N;
   int* ipiv;
   int* info;
-  PanelSlot* slots;
-  PanelShared* shared_rows;
-  unsigned* bar;
+  PanelHdr* hdrs;
+  PanelRow* rows;
+  PanelRow* rowj;
+  double* linv;    // inverses of the 128 x 128 diagonal blocks of L (unit lower), block b at b*IB*IB
+  int64_t swap_c0, swap_c1;  // columns that receive a leaf's interchanges right after the leaf
   cudaStream_t st;
 };
+
+static unsigned g_panel_epoch = 1;
 
 static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   // panel = A[j0 : j0+m, j0 : j0+w]
   double* P = L.A + j0 + j0 * L.lda;
   int G = (int)((m + PR - 1) / PR);
-  LLA_CUDA(cudaMemsetAsync(L.bar, 0, sizeof(unsigned), L.st));
   int64_t m_ = m, lda_ = L.lda, off_ = j0;
   int w_ = w;
   int* ipiv_ = L.ipiv;
   int* info_ = L.info;
-  PanelSlot* slots_ = L.slots;
-  PanelShared* sr_ = L.shared_rows;
-  unsigned* bar_ = L.bar;
-  void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &slots_, &sr_, &bar_};
-  LLA_CUDA(cudaLaunchCooperativeKernel((void*)lla_dgetf2_panel_kernel, dim3(G), dim3(PR), args, 0, L.st));
+  PanelHdr* h_ = L.hdrs;
+  PanelRow* r_ = L.rows;
+  PanelRow* rj_ = L.rowj;
+  unsigned epoch = g_panel_epoch++ & 0x03ffffffu;
+  if (epoch == 0) epoch = g_panel_epoch++ & 0x03ffffffu;
+  void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &h_, &r_, &rj_, &epoch};
+  LLA_CUDA(cudaLaunchCooperativeKernel((void*)lla_dgetf2_panel_kernel, dim3(G), dim3(PR), args, PANEL_SMEM, L.st));
   count_launch();
-  // interchange the rest of the rows now: columns [0, j0) and [j0+w, N)
+  // interchange the other columns of the swap window now: [swap_c0, j0) and [j0+w, swap_c1)
   int64_t npiv = m < w ? m : w;
-  LLA_TRY(dlaswp_skip_dev(L.N, j0, j0 + w, L.A, L.lda, j0, j0 + npiv, L.ipiv, true, L.st, nullptr));
+  LLA_TRY(dlaswp_skip_dev(L.swap_c1 - L.swap_c0, j0 - L.swap_c0, j0 + w - L.swap_c0, L.A + L.swap_c0 * L.lda, L.lda,
+                          j0, j0 + npiv, L.ipiv, true, L.st, nullptr));
   return 0;
 }
 
+// m x n block whose top-left corner is the diagonal element (j0, j0)
 static int lu_rec(const LuCtx& L, int64_t j0, int64_t m, int64_t n) {
   if (m <= 0 || n <= 0) return 0;
   if (n <= PW) return lu_leaf(L, j0, m, (int)n);
-  int64_t mn = m < n ? m : n;
-  int64_t n1 = mn > PW ? ((mn / 2) / PW) * PW : mn;
-  if (n1 < PW && mn > PW) n1 = PW;
-  int64_t n2 = n - n1;
+  const int64_t mn = m < n ? m : n;
+  // split on multiples of 128 above 128 columns (GEMM-only solves with the inverted diagonal
+  // blocks of L), on multiples of 32 inside a 128-column block (substitution leaves)
+  int64_t n1;
+  if (mn > IB) n1 = (mn >= 2 * IB) ? ((mn / 2) / IB) * IB : IB;
+  else if (mn > PW) n1 = (mn >= 2 * PW) ? ((mn / 2) / PW) * PW : PW;
+  else n1 = mn;
+  const int64_t n2 = n - n1;
   LLA_TRY(lu_rec(L, j0, m, n1));
   double* A11 = L.A + j0 + j0 * L.lda;
   double* A12 = A11 + n1 * L.lda;
   double* A21 = A11 + n1;
   double* A22 = A12 + n1;
-  // A12 <- L11^{-1} A12 ; A22 <- A22 - A21 A12
-  LLA_TRY(dtrsm_left_dev(false, 0, true, n1, n2, A11, L.lda, A12, L.lda, L.st));
-  if (m > n1) {
-    LLA_TRY(dgemm_dev(0, 0, m - n1, n2, n1, -1.0, A21, L.lda, A12, L.lda, 1.0, A22, L.lda, TRI_FULL, L.st));
-    LLA_TRY(lu_rec(L, j0 + n1, m - n1, n2));
+  if (n2 > 0) {
+    // A12 <- L11^{-1} A12 ; A22 <- A22 - A21 A12
+    if (n1 % IB == 0 && j0 % IB == 0)
+      LLA_TRY(dtrsm_left_inv_dev(false, 0, n1, n2, A11, L.lda, L.linv + (j0 / IB) * IB * IB, A12, L.lda, L.st));
+    else
+      LLA_TRY(dtrsm_left_dev(false, 0, true, n1, n2, A11, L.lda, A12, L.lda, L.st));
+    if (m > n1) {
+      LLA_TRY(dgemm_dev(0, 0, m - n1, n2, n1, -1.0, A21, L.lda, A12, L.lda, 1.0, A22, L.lda, TRI_FULL, L.st));
+      LLA_TRY(lu_rec(L, j0 + n1, m - n1, n2));
+    }
+  }
+  // a 128-column block of L is final once the node that covers exactly that block returns:
+  // invert its unit-lower diagonal block for the GEMM-only solves of the levels above
+  if (j0 % IB == 0 && n <= IB && (n == IB || j0 + n == L.N || m <= n)) {
+    int64_t r = mn;  // rows/cols of the diagonal block that exist
+    LLA_TRY(dtrtri_blocks_dev(false, true, r, A11, L.lda, L.linv + (j0 / IB) * IB * IB, L.st));
   }
   return 0;
 }
 
-__global__ void lla_iota_ipiv_kernel(int* ipiv, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) ipiv[i] = (int)(i + 1);
+// columns [c0, c1) right of panel (k, kb): interchanges, U12 = L11^-1 A12, A22 -= A21 U12
+static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st) {
+  if (c1 <= c0) return 0;
+  const int64_t nc = c1 - c0;
+  double* A11 = L.A + k + k * L.lda;
+  double* A12 = L.A + k + c0 * L.lda;
+  LLA_TRY(dlaswp_dev(nc, L.A + c0 * L.lda, L.lda, k, k + kb, L.ipiv, true, st));
+  LLA_TRY(dtrsm_left_inv_dev(false, 0, kb, nc, A11, L.lda, L.linv + (k / IB) * IB * IB, A12, L.lda, st));
+  if (L.M > k + kb)
+    LLA_TRY(dgemm_dev(0, 0, L.M - k - kb, nc, kb, -1.0, A11 + kb, L.lda, A12, L.lda, 1.0, A12 + kb, L.lda, TRI_FULL, st));
+  return 0;
+}
+
+// Blocked right-looking driver with one panel of look-ahead: panel k+1 (recursive, cooperative
+// leaf kernels) runs on the high-priority panel stream while the trailing update of step k is
+// still running on the main stream; the interchanges of the columns left of a panel go to a third
+// stream, since nothing depends on them until the end.
+static int lu_blocked(LuCtx L) {
+  Context* c = ctx();
+  const int64_t NB = 512;
+  const int64_t mn = L.M < L.N ? L.M : L.N;
+  if (mn <= 2 * NB) {
+    L.swap_c0 = 0; L.swap_c1 = L.N;
+    return lu_rec(L, 0, L.M, L.N);
+  }
+  cudaStream_t s1 = L.st, s2 = c->aux, s3 = c->h2d;
+  cudaEvent_t ev_start = c->ev[3], ev_panel = c->ev[4], ev_a = c->ev[5], ev_b = c->ev[6], ev_left = c->ev[7];
+  LLA_CUDA(cudaEventRecord(ev_start, s1));
+  LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+  bool have_b = false;
+  for (int64_t k = 0; k < mn; k += NB) {
+    const int64_t kb = (mn - k) < NB ? (mn - k) : NB;
+    // ---- panel k on s2
+    LuCtx P = L;
+    P.st = s2; P.swap_c0 = k; P.swap_c1 = k + kb;
+    LLA_TRY(lu_rec(P, k, L.M - k, kb));
+    LLA_CUDA(cudaEventRecord(ev_panel, s2));
+    // ---- interchanges of the finished columns [0, k) on s3 (after the update that still reads them)
+    if (k > 0) {
+      LLA_CUDA(cudaStreamWaitEvent(s3, ev_panel, 0));
+      if (have_b) LLA_CUDA(cudaStreamWaitEvent(s3, ev_b, 0));
+      LLA_TRY(dlaswp_dev(k, L.A, L.lda, k, k + kb, L.ipiv, true, s3));
+      LLA_CUDA(cudaEventRecord(ev_left, s3));
+    }
+    // ---- trailing update of step k on s1: next panel's columns first, then the rest
+    const int64_t c0 = k + kb;
+    if (c0 >= L.N) break;
+    LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
+    const int64_t next_kb = (k + kb < mn) ? ((mn - c0) < NB ? (mn - c0) : NB) : 0;
+    const int64_t c1 = c0 + next_kb;
+    LLA_TRY(lu_update_cols(L, k, kb, c0, c1, s1));
+    LLA_CUDA(cudaEventRecord(ev_a, s1));
+    LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
+    LLA_TRY(lu_update_cols(L, k, kb, c1, L.N, s1));
+    LLA_CUDA(cudaEventRecord(ev_b, s1));
+    have_b = true;
+  }
+  LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
+  if (mn > NB) LLA_CUDA(cudaStreamWaitEvent(s1, ev_left, 0));
+  return 0;
 }
 
 int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st) {
@@ -341,33 +433,46 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   if (m <= 0 || n <= 0) return 0;
   int maxG = (int)((m + PR - 1) / PR);
   // co-residency bound of the cooperative panel kernel
-  int per_sm = 0;
-  LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel, PR, 0));
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel, PR, PANEL_SMEM));
+  }
   if ((int64_t)per_sm * c->sm_count < maxG) {
     set_error(__FILE__, __LINE__, "dgetrf: panel too tall for one cooperative launch", (int)m);
     return LLACUDA_ERR_BAD_ARG;
   }
-  size_t need = sizeof(PanelSlot) * 2 * (size_t)maxG + sizeof(PanelShared) * 2 + 256;
-  LLA_TRY(ensure_workspace(need));
-  char* ws = (char*)c->ws;
+  const int64_t mn = m < n ? m : n;
+  Arena ar;
+  LLA_TRY(ar.reserve(sizeof(PanelHdr) * 2 * maxG + sizeof(PanelRow) * (2 * maxG + 2) + tinv_bytes(mn) + 4096));
   LuCtx L;
   L.A = A; L.lda = lda; L.M = m; L.N = n; L.ipiv = ipiv; L.info = info_dev; L.st = st;
-  L.bar = (unsigned*)ws;
-  L.shared_rows = (PanelShared*)(ws + 256);
-  L.slots = (PanelSlot*)(ws + 256 + sizeof(PanelShared) * 2);
-  return lu_rec(L, 0, m, n);
+  L.swap_c0 = 0; L.swap_c1 = n;
+  L.hdrs = (PanelHdr*)ar.take(sizeof(PanelHdr) * 2 * maxG);
+  L.rows = (PanelRow*)ar.take(sizeof(PanelRow) * 2 * maxG);
+  L.rowj = (PanelRow*)ar.take(sizeof(PanelRow) * 2);
+  L.linv = (double*)ar.take(tinv_bytes(mn));
+  return lu_blocked(L);
 }
 
 int dgetrs_dev(int op, int64_t n, int64_t nrhs, const double* A, int64_t lda, const int* ipiv, double* B,
                int64_t ldb, cudaStream_t st, const int* abort_flag) {
   if (n <= 0 || nrhs <= 0) return 0;
+  // inverses of the 128 x 128 diagonal blocks of L and of U (two batched launches); both
+  // triangular solves are then GEMMs only
+  Arena ar;
+  LLA_TRY(ar.reserve(2 * tinv_bytes(n) + 1024));
+  double* linv = (double*)ar.take(tinv_bytes(n));
+  double* uinv = (double*)ar.take(tinv_bytes(n));
+  LLA_TRY(dtrtri_blocks_dev(false, true, n, A, lda, linv, st, abort_flag));
+  LLA_TRY(dtrtri_blocks_dev(true, false, n, A, lda, uinv, st, abort_flag));
   if (op == 0) {
     LLA_TRY(dlaswp_dev(nrhs, B, ldb, 0, n, ipiv, true, st, abort_flag));
-    LLA_TRY(dtrsm_left_dev(false, 0, true, n, nrhs, A, lda, B, ldb, st, abort_flag));
-    LLA_TRY(dtrsm_left_dev(true, 0, false, n, nrhs, A, lda, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(false, 0, n, nrhs, A, lda, linv, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(true, 0, n, nrhs, A, lda, uinv, B, ldb, st, abort_flag));
   } else {
-    LLA_TRY(dtrsm_left_dev(true, 1, false, n, nrhs, A, lda, B, ldb, st, abort_flag));
-    LLA_TRY(dtrsm_left_dev(false, 1, true, n, nrhs, A, lda, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(true, 1, n, nrhs, A, lda, uinv, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(false, 1, n, nrhs, A, lda, linv, B, ldb, st, abort_flag));
     LLA_TRY(dlaswp_dev(nrhs, B, ldb, 0, n, ipiv, false, st, abort_flag));
   }
   return 0;

@@ -4,64 +4,100 @@
 // untransposed row-major buffer, which yields the row-major lower factor) and `dpotrs_`
 // (solve on a cholesky object, :296-301).
 //
-// Recursive formulation (as LAPACK's DPOTRF2): A11 = U11^T U11 ; U12 = U11^-T A12 (TRSM) ;
-// A22 -= U12^T U12 (DMMA GEMM restricted to the upper triangle) ; recurse on A22.  Only the named
-// triangle is ever written.  A non-positive or NaN pivot stores INFO = its 1-based index in a
+// Recursive formulation (as LAPACK's DPOTRF2) on multiples of 128: A11 = U11^T U11 ; U12 = U11^-T A12 ;
+// A22 -= U12^T U12 (DMMA GEMM restricted to the upper triangle) ; recurse on A22.  Leaves are
+// 128 x 128 blocks factored by one CTA in shared memory, which also leaves inv(U_ii) behind so
+// that every triangular solve above the leaves is a DMMA GEMM.  Only the named triangle is ever
+// written.  A non-positive or NaN pivot stores INFO = its 1-based index in a
 // device flag that every later kernel of the call checks, so, as in LAPACK, nothing after the
 // failing minor is modified.  UPLO='L' runs the same code on the in-place transpose.
 #include "internal.h"
+#include "tri128.cuh"
 #include "../../include/llacuda.h"
 
 namespace llacuda {
 
-constexpr int CL = 32;  // leaf size
-
-// one CTA of 32x32 threads factors the upper triangle of an n x n (n <= 32) block
-__global__ void __launch_bounds__(CL * CL) lla_dpotf2_leaf_kernel(int n, double* __restrict__ A, int64_t lda, int off,
-                                                              int* __restrict__ info) {
+// One CTA factors an r x r (r <= 128) diagonal block held in shared memory as L = U^T, writes U
+// back over the upper triangle of A and leaves inv(U) in `uinv` (128 x 128, upper, zero below) for
+// the GEMM-only triangular solves of the levels above.
+__global__ void __launch_bounds__(T128_THREADS) lla_dpotrf128_kernel(int r, double* __restrict__ A, int64_t lda,
+                                                                     double* __restrict__ uinv, int off,
+                                                                     int* __restrict__ info) {
   if (*info != 0) return;
-  __shared__ double s[CL][CL + 1];
-  __shared__ int s_fail;
-  const int i = threadIdx.x, j = threadIdx.y;  // element (i, j), i = row
-  const bool in = i < n && j < n && i <= j;
-  s[i][j] = in ? A[i + (int64_t)j * lda] : 0.0;
-  if (i == 0 && j == 0) s_fail = 0;
+  extern __shared__ __align__(16) double sm128[];
+  double* S = sm128;
+  double* tmp = sm128 + T128 * T128_SP;
+  const int tid = threadIdx.x;
+  tri128_load_lower(S, A, lda, r, /*src_upper=*/true, /*unit=*/false, tid);
   __syncthreads();
-  for (int k = 0; k < n; k++) {
-    double d = s[k][k];
-    if (!(d > 0.0)) {  // also catches NaN, as DPOTF2's  ajj <= 0 .or. disnan(ajj)
-      if (i == 0 && j == 0) s_fail = k + 1;
-      break;  // d is read by every thread from the same location: uniform exit
-    }
-    double r = sqrt(d);
-    __syncthreads();
-    if (i == k && j == k) s[k][k] = r;
-    if (i == k && j > k && j < n) s[k][j] = s[k][j] / r;
-    __syncthreads();
-    if (i > k && j >= i && j < n) s[i][j] = fma(-s[k][i], s[k][j], s[i][j]);
-    __syncthreads();
+  const int fail = potrf128_lower_smem(S, r, tid);
+  if (fail != 0) {  // leading minor off+fail is not positive definite: flag it, later kernels skip
+    if (tid == 0) *info = off + fail;
+    return;
   }
+  tri128_store(S, A, lda, r, /*dst_upper=*/true, /*zero_other=*/false, tid);
   __syncthreads();
-  if (in) A[i + (int64_t)j * lda] = s[i][j];
-  if (i == 0 && j == 0 && s_fail != 0) *info = off + s_fail;
+  trtri128_lower_smem(S, tmp, /*unit=*/false, tid);
+  tri128_store(S, uinv, IB, IB, /*dst_upper=*/true, /*zero_other=*/true, tid);
 }
 
-static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, int* info, cudaStream_t st) {
+static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, double* uinv, int* info, cudaStream_t st) {
   if (n <= 0) return 0;
-  if (n <= CL) {
-    lla_dpotf2_leaf_kernel<<<1, dim3(CL, CL), 0, st>>>((int)n, A, lda, (int)off, info);
+  if (n <= IB) {
+    lla_dpotrf128_kernel<<<1, T128_THREADS, T128_SMEM, st>>>((int)n, A, lda, uinv, (int)off, info);
     count_launch();
     LLA_CUDA(cudaGetLastError());
     return 0;
   }
-  int64_t n1 = ((n / 2 + CL - 1) / CL) * CL;
+  int64_t n1 = ((n / 2 + IB - 1) / IB) * IB;
   int64_t n2 = n - n1;
   double* A12 = A + n1 * lda;
   double* A22 = A12 + n1;
-  LLA_TRY(potrf_rec(n1, A, lda, off, info, st));
-  LLA_TRY(dtrsm_left_dev(true, 1, false, n1, n2, A, lda, A12, lda, st, info));
+  LLA_TRY(potrf_rec(n1, A, lda, off, uinv, info, st));
+  LLA_TRY(dtrsm_left_inv_dev(true, 1, n1, n2, A, lda, uinv, A12, lda, st, info));
   LLA_TRY(dgemm_dev(1, 0, n2, n2, n1, -1.0, A12, lda, A12, lda, 1.0, A22, lda, TRI_UPPER, st, info));
-  LLA_TRY(potrf_rec(n2, A22, lda, off + n1, info, st));
+  LLA_TRY(potrf_rec(n2, A22, lda, off + n1, uinv + (n1 / IB) * IB * IB, info, st));
+  return 0;
+}
+
+// Blocked right-looking driver with one panel of look-ahead.  Step k factors the diagonal block
+// (recursively, down to the shared-memory leaves) and solves for its block row on the high-priority
+// panel stream while the previous step's trailing update is still running on the main stream: the
+// update of step k-1 is split into (a) the block row that panel k needs and (b) everything below.
+static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* info, cudaStream_t s1) {
+  Context* c = ctx();
+  const int64_t NB = 512;
+  if (n <= 2 * NB) return potrf_rec(n, A, lda, 0, uinv, info, s1);
+  cudaStream_t s2 = c->aux;
+  cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2];
+  LLA_CUDA(cudaEventRecord(ev_start, s1));
+  LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+  for (int64_t k = 0; k < n; k += NB) {
+    const int64_t kb = (n - k) < NB ? (n - k) : NB;
+    const int64_t n2 = n - k - kb;
+    double* Akk = A + k + k * lda;
+    double* Arow = Akk + kb * lda;             // block row right of the diagonal block
+    double* uk = uinv + (k / IB) * IB * IB;
+    // ---- panel k on s2 (its inputs were produced by part (a) of the previous update)
+    LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, s2));
+    if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, s2, info));
+    LLA_CUDA(cudaEventRecord(ev_panel, s2));
+    if (n2 <= 0) break;
+    // ---- trailing update of step k on s1
+    LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
+    const int64_t kb_next = n2 < NB ? n2 : NB;
+    double* Anext = Arow + kb;                   // A[k+kb, k+kb]
+    // (a) block row of the next panel: rows [k+kb, k+kb+kb_next), columns [k+kb, n)
+    LLA_TRY(dgemm_dev(1, 0, kb_next, n2, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, s1, info));
+    LLA_CUDA(cudaEventRecord(ev_row, s1));
+    LLA_CUDA(cudaStreamWaitEvent(s2, ev_row, 0));
+    // (b) the rest: rows [k+kb+kb_next, n)
+    const int64_t n3 = n2 - kb_next;
+    if (n3 > 0)
+      LLA_TRY(dgemm_dev(1, 0, n3, n3, kb, -1.0, Arow + kb_next * lda, lda, Arow + kb_next * lda, lda, 1.0,
+                        Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info));
+  }
+  LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   return 0;
 }
 
@@ -69,8 +105,16 @@ int dpotrf_dev(bool upper, int64_t n, double* A, int64_t lda, int* info_dev, cud
   if (!ctx()) return LLACUDA_ERR_NO_DEVICE;
   LLA_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
   if (n <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    LLA_CUDA(cudaFuncSetAttribute(lla_dpotrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T128_SMEM));
+    configured = true;
+  }
+  Arena ar;
+  LLA_TRY(ar.reserve(tinv_bytes(n)));
+  double* uinv = (double*)ar.take(tinv_bytes(n));
   if (!upper) LLA_TRY(dtranspose_inplace_dev(n, A, lda, st));
-  LLA_TRY(potrf_rec(n, A, lda, 0, info_dev, st));
+  LLA_TRY(potrf_blocked(n, A, lda, uinv, info_dev, st));
   if (!upper) LLA_TRY(dtranspose_inplace_dev(n, A, lda, st));
   return 0;
 }
@@ -78,12 +122,18 @@ int dpotrf_dev(bool upper, int64_t n, double* A, int64_t lda, int* info_dev, cud
 int dpotrs_dev(bool upper, int64_t n, int64_t nrhs, const double* A, int64_t lda, double* B, int64_t ldb,
                cudaStream_t st, const int* abort_flag) {
   if (n <= 0 || nrhs <= 0) return 0;
+  // inverses of the 128 x 128 diagonal blocks of the factor (one batched launch), then both
+  // triangular solves are GEMMs only
+  Arena ar;
+  LLA_TRY(ar.reserve(tinv_bytes(n)));
+  double* tinv = (double*)ar.take(tinv_bytes(n));
+  LLA_TRY(dtrtri_blocks_dev(upper, false, n, A, lda, tinv, st, abort_flag));
   if (upper) {  // A = U^T U :  U^T y = b ; U x = y
-    LLA_TRY(dtrsm_left_dev(true, 1, false, n, nrhs, A, lda, B, ldb, st, abort_flag));
-    LLA_TRY(dtrsm_left_dev(true, 0, false, n, nrhs, A, lda, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(true, 1, n, nrhs, A, lda, tinv, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(true, 0, n, nrhs, A, lda, tinv, B, ldb, st, abort_flag));
   } else {      // A = L L^T :  L y = b ; L^T x = y
-    LLA_TRY(dtrsm_left_dev(false, 0, false, n, nrhs, A, lda, B, ldb, st, abort_flag));
-    LLA_TRY(dtrsm_left_dev(false, 1, false, n, nrhs, A, lda, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(false, 0, n, nrhs, A, lda, tinv, B, ldb, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(false, 1, n, nrhs, A, lda, tinv, B, ldb, st, abort_flag));
   }
   return 0;
 }

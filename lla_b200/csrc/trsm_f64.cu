@@ -6,6 +6,7 @@
 // 32 x 32 diagonal blocks are solved by substitution (column-oriented, the order of netlib xTRSM)
 // with one thread per right-hand side holding its 32 unknowns in registers.
 #include "internal.h"
+#include "tri128.cuh"
 #include "../../include/llacuda.h"
 
 namespace llacuda {
@@ -25,6 +26,7 @@ __global__ void __launch_bounds__(TL_COLS) lla_dtrsm_leaf_kernel(int m, int64_t 
   const int tid = threadIdx.x;
   const int64_t c0 = (int64_t)blockIdx.x * TL_COLS;
 
+#pragma unroll
   for (int idx = tid; idx < TL * TL; idx += TL_COLS) {
     int i = idx % TL, k = idx / TL;  // consecutive threads walk down a column of T
     double v = (i == k) ? 1.0 : 0.0;
@@ -33,11 +35,15 @@ __global__ void __launch_bounds__(TL_COLS) lla_dtrsm_leaf_kernel(int m, int64_t 
     else e[i * (TL + 1) + k] = v;
   }
   const int lane = tid & 31, w = tid >> 5;
-  for (int c = w; c < TL_COLS; c += TL_COLS / 32) {
-    int64_t gc = c0 + c;
-    double v = 0.0;
-    if (gc < n && lane < m) v = B[lane + gc * ldb];
-    bs[c * (TL + 1) + lane] = v;
+  {
+    double v[TL_COLS / 2];  // all loads of the slab in flight before the first store
+#pragma unroll
+    for (int q = 0; q < TL_COLS / 2; q++) {
+      int64_t gc = c0 + w + 2 * q;
+      v[q] = (gc < n && lane < m) ? B[lane + gc * ldb] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < TL_COLS / 2; q++) bs[(w + 2 * q) * (TL + 1) + lane] = v[q];
   }
   __syncthreads();
 
@@ -64,6 +70,7 @@ __global__ void __launch_bounds__(TL_COLS) lla_dtrsm_leaf_kernel(int m, int64_t 
 #pragma unroll
   for (int i = 0; i < TL; i++) bs[tid * (TL + 1) + i] = x[i];
   __syncthreads();
+#pragma unroll
   for (int c = w; c < TL_COLS; c += TL_COLS / 32) {
     int64_t gc = c0 + c;
     if (gc < n && lane < m) B[lane + gc * ldb] = bs[c * (TL + 1) + lane];
@@ -111,6 +118,73 @@ int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n, const do
     if (upper) LLA_TRY(dgemm_dev(0, 0, m1, n, m2, -1.0, T12, ldt, B2, ldb, 1.0, B1, ldb, TRI_FULL, st, abort_flag));
     else LLA_TRY(dgemm_dev(1, 0, m1, n, m2, -1.0, T21, ldt, B2, ldb, 1.0, B1, ldb, TRI_FULL, st, abort_flag));
     LLA_TRY(dtrsm_left_dev(upper, op, unit, m1, n, T11, ldt, B1, ldb, st, abort_flag));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ inverse-based solves
+// One CTA per IB x IB diagonal block: Tinv_b = inv(T_bb) (same triangle, other triangle zero).
+__global__ void __launch_bounds__(T128_THREADS) lla_dtrtri_blocks_kernel(int64_t m, const double* __restrict__ T,
+                                                                         int64_t ldt, double* __restrict__ Tinv,
+                                                                         bool upper, bool unit, const int* abort_flag) {
+  if (abort_flag != nullptr && *abort_flag != 0) return;
+  extern __shared__ __align__(16) double sm128[];
+  double* S = sm128;
+  double* tmp = sm128 + T128 * T128_SP;
+  const int64_t b = blockIdx.x;
+  const int64_t rem = m - b * IB;
+  const int r = (int)(rem < IB ? rem : IB);
+  const double* Tb = T + b * IB + b * IB * ldt;
+  tri128_load_lower(S, Tb, ldt, r, upper, unit, threadIdx.x);
+  __syncthreads();
+  trtri128_lower_smem(S, tmp, unit, threadIdx.x);
+  tri128_store(S, Tinv + b * IB * IB, IB, IB, upper, true, threadIdx.x);
+}
+
+int dtrtri_blocks_dev(bool upper, bool unit, int64_t m, const double* T, int64_t ldt, double* Tinv, cudaStream_t st,
+                      const int* abort_flag) {
+  if (m <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    LLA_CUDA(cudaFuncSetAttribute(lla_dtrtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T128_SMEM));
+    configured = true;
+  }
+  unsigned grid = (unsigned)((m + IB - 1) / IB);
+  lla_dtrtri_blocks_kernel<<<grid, T128_THREADS, T128_SMEM, st>>>(m, T, ldt, Tinv, upper, unit, abort_flag);
+  count_launch();
+  LLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// op(T) X = B with the diagonal-block inverses at hand: recursive halving on multiples of IB, the
+// leaves are in-place products B_i <- op(Tinv_i) B_i on the DMMA GEMM (one 128-row tile per column
+// slab, so the aliasing of B and C is safe), the couplings are ordinary GEMMs.
+int dtrsm_left_inv_dev(bool upper, int op, int64_t m, int64_t n, const double* T, int64_t ldt, const double* Tinv,
+                       double* B, int64_t ldb, cudaStream_t st, const int* abort_flag) {
+  if (m <= 0 || n <= 0) return 0;
+  const bool trans = op != 0;
+  const bool eff_lower = (upper == trans);
+  if (m <= IB)
+    return dgemm_dev(trans ? 1 : 0, 0, m, n, m, 1.0, Tinv, IB, B, ldb, 0.0, B, ldb, TRI_FULL, st, abort_flag,
+                     GEMM_INPLACE_B);
+  int64_t m1 = ((m / 2 + IB - 1) / IB) * IB;
+  int64_t m2 = m - m1;
+  const double* T22 = T + m1 + m1 * ldt;
+  const double* T21 = T + m1;
+  const double* T12 = T + m1 * ldt;
+  const double* Tinv2 = Tinv + (m1 / IB) * IB * IB;
+  double* B1 = B;
+  double* B2 = B + m1;
+  if (eff_lower) {
+    LLA_TRY(dtrsm_left_inv_dev(upper, op, m1, n, T, ldt, Tinv, B1, ldb, st, abort_flag));
+    if (!upper) LLA_TRY(dgemm_dev(0, 0, m2, n, m1, -1.0, T21, ldt, B1, ldb, 1.0, B2, ldb, TRI_FULL, st, abort_flag));
+    else LLA_TRY(dgemm_dev(1, 0, m2, n, m1, -1.0, T12, ldt, B1, ldb, 1.0, B2, ldb, TRI_FULL, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(upper, op, m2, n, T22, ldt, Tinv2, B2, ldb, st, abort_flag));
+  } else {
+    LLA_TRY(dtrsm_left_inv_dev(upper, op, m2, n, T22, ldt, Tinv2, B2, ldb, st, abort_flag));
+    if (upper) LLA_TRY(dgemm_dev(0, 0, m1, n, m2, -1.0, T12, ldt, B2, ldb, 1.0, B1, ldb, TRI_FULL, st, abort_flag));
+    else LLA_TRY(dgemm_dev(1, 0, m1, n, m2, -1.0, T21, ldt, B2, ldb, 1.0, B1, ldb, TRI_FULL, st, abort_flag));
+    LLA_TRY(dtrsm_left_inv_dev(upper, op, m1, n, T, ldt, Tinv, B1, ldb, st, abort_flag));
   }
   return 0;
 }

@@ -176,3 +176,50 @@ def test_cholesky_not_pd_index_and_untouched_triangle():
     with pytest.raises(O.LapackFailure) as eo:
         O.cholesky(bad, O.netlib())
     assert e.value.info == eo.value.info == 101
+
+
+@pytest.mark.parametrize("shape", [(1300, 1300), (1500, 1100), (1100, 1500), (2111, 2111)])
+def test_lu_blocked_lookahead_path_vs_oracle(shape):
+    """min(m, n) > 1024 takes the blocked driver with look-ahead (three streams): ipiv must still be
+    bit-exact with both oracles, and P A = L U must hold."""
+    rng = np.random.default_rng(shape[0] + 3 * shape[1])
+    a = rng.uniform(0, 10, shape)
+    f = L.lu(a)
+    r2 = O.lu(a, O.openblas())
+    assert np.array_equal(f.ipiv_internal, r2.ipiv_internal)
+    if shape[0] <= 1500:
+        r1 = O.lu(a, O.netlib())
+        assert np.array_equal(f.ipiv_internal, r1.ipiv_internal)
+    scale = max(shape) * EPS * np.abs(r2.lu).max() * 50
+    assert np.max(np.abs(f.lu - r2.lu)) <= scale
+    if shape[0] == shape[1]:
+        p = L.ipiv(f.ipiv_internal)
+        rec = L.lu_l(f) @ L.lu_u(f)
+        assert np.linalg.norm(a[p, :] - rec) / (shape[0] * EPS * np.linalg.norm(a)) <= 10
+
+
+@pytest.mark.parametrize("n", [1100, 1700, 2304])
+def test_cholesky_blocked_lookahead_path(n):
+    rng = np.random.default_rng(n)
+    g = rng.uniform(0, 1, (n, n))
+    spd = g @ g.T + n * np.eye(n)
+    c = L.cholesky(spd)
+    r = O.cholesky(spd, O.openblas())
+    assert np.max(np.abs(c.left - r.left)) <= 20 * n * EPS * np.abs(r.left).max()
+    assert np.linalg.norm(c.left @ c.left.T - spd) / (n * EPS * np.linalg.norm(spd)) <= 10
+    b = rng.uniform(0, 1, (n, 3))
+    assert residual(spd, L.solve(c, b), b) <= 10
+    bad = spd.copy()
+    bad[n - 7, n - 7] = -1.0
+    with pytest.raises(L.LapackFailure) as e:
+        L.cholesky(bad)
+    assert e.value.info == n - 6
+
+
+def test_solve_large_residual():
+    rng = np.random.default_rng(77)
+    n, nrhs = 2500, 64
+    a, b = rng.uniform(0, 10, (n, n)), rng.uniform(0, 10, (n, nrhs))
+    x = L.solve(a, b)
+    assert residual(a, x, b) <= 10
+    assert np.allclose(x, O.solve(a, b, O.openblas()), rtol=1e-6, atol=1e-8)
