@@ -22,11 +22,13 @@
 
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 
 namespace llacuda {
 
 constexpr int PW = 32;     // leaf panel width (columns held in registers per row)
-constexpr int PR = 256;    // rows (= threads) per CTA
+constexpr int PR = 128;    // rows (= threads) per CTA
 
 // Cross-CTA exchange uses self-validating 8-byte words (32 bits of payload + a 32-bit tag, the
 // NCCL "LL" idea): an aligned 8-byte store is single-copy atomic, so a reader that sees the
@@ -56,10 +58,10 @@ constexpr size_t PANEL_SMEM = (size_t)PW * PPITCH * sizeof(double);
 // owns row t; warp 0 runs the cross-CTA exchange of every column.  These kernels are bound by
 // instruction latency (a handful of warps per SM), so the per-column instruction count is what
 // is being minimised here -- no unrolled register-array selects, real loops with dynamic bounds.
-__global__ void __launch_bounds__(PR, 2) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
+__global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
                                                                  int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
                                                                  PanelHdr* __restrict__ hdrs, PanelRow* __restrict__ rows,
-                                                                 PanelRow* __restrict__ rowj, unsigned epoch) {
+                                                                 PanelRow* __restrict__ rowj, unsigned epoch, long long* dbg) {
   extern __shared__ __align__(16) double S[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -69,15 +71,16 @@ __global__ void __launch_bounds__(PR, 2) lla_dgetf2_panel_kernel(double* __restr
   const bool live = grow < m;
   const int nsteps = (int)(m < w ? m : w);
 
-  {
-    double v[PW];
 #pragma unroll
-    for (int c = 0; c < PW; c++) v[c] = (live && c < w) ? A[grow + (int64_t)c * lda] : 0.0;
+  for (int c8 = 0; c8 < PW; c8 += 8) {  // 8 loads in flight per thread keeps the register count low
+    double v[8];
 #pragma unroll
-    for (int c = 0; c < PW; c++) S[c * PPITCH + tid] = v[c];
+    for (int c = 0; c < 8; c++) v[c] = (live && c8 + c < w) ? A[grow + (int64_t)(c8 + c) * lda] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) S[(c8 + c) * PPITCH + tid] = v[c];
   }
 
-  __shared__ double s_val[PR / 32];
+  __shared__ unsigned long long s_key[PR / 32];
   __shared__ int s_row[PR / 32];
   __shared__ double s_prow[PW];
   __shared__ double s_rowj[PW];
@@ -90,75 +93,84 @@ __global__ void __launch_bounds__(PR, 2) lla_dgetf2_panel_kernel(double* __restr
   for (int j = 0; j < nsteps; j++) {
     const int par = j & 1;
     const unsigned tag = (epoch << 6) | (unsigned)(j + 1);
-    // ---- 1. candidate of this warp: first row (>= j) with the largest |a[j]|; NaN only wins as row j
-    double v = -1.0;
-    int r = 0x7fffffff;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+    if (dbg) t0 = clock64();
+    // ---- 1. candidate of this warp: first row (>= j) with the largest |a[j]|; NaN only wins as row j.
+    // The magnitude is turned into an order-preserving 64-bit key (0 = no number here) so that the
+    // arg-max is three 32-bit REDUX operations instead of five rounds of 64-bit shuffles.
+    unsigned long long key = 0ull;
+    unsigned r = 0x7fffffffu;
     if (live && grow >= j) {
       double x = fabs(S[j * PPITCH + tid]);
       bool isn = (x != x);
-      if (grow == j && isn) v = INFINITY;  // IDAMAX: dmax = NaN, nothing compares greater
-      else v = isn ? -1.0 : x;
-      r = (int)grow;
+      if (grow == j && isn) x = INFINITY;  // IDAMAX: dmax = NaN, nothing compares greater
+      if (x == x) key = (unsigned long long)__double_as_longlong(x) + 1ull;
+      r = (unsigned)grow;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, v, o);
-      int orow = __shfl_xor_sync(0xffffffffu, r, o);
-      if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+    {
+      unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+      unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      bool c1 = hi == mh;
+      unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+      bool c2 = c1 && lo == ml;
+      unsigned rm = __reduce_min_sync(0xffffffffu, c2 ? r : 0x7fffffffu);
+      if (lane == 0) { s_key[warp] = ((unsigned long long)mh << 32) | ml; s_row[warp] = (int)rm; }
     }
-    if (lane == 0) { s_val[warp] = v; s_row[warp] = r; }
     __syncthreads();
+    if (dbg) t1 = clock64();
     // ---- 2. warp 0: CTA candidate, publish, wait for every CTA, pick the winner, fetch its row
     if (warp == 0) {
-      double bv = (lane < PR / 32) ? s_val[lane] : -3.0;
-      int br = (lane < PR / 32) ? s_row[lane] : 0x7fffffff;
-#pragma unroll
-      for (int o = PR / 64; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        int orow = __shfl_xor_sync(0xffffffffu, br, o);
-        if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
-      }
-      bv = __shfl_sync(0xffffffffu, bv, 0);
-      br = __shfl_sync(0xffffffffu, br, 0);
-      const int lr = br - (int)row0;  // the CTA's candidate row is always one of its own live rows
+      unsigned long long k8 = (lane < PR / 32) ? s_key[lane] : 0ull;
+      unsigned r8 = (lane < PR / 32) ? (unsigned)s_row[lane] : 0x7fffffffu;
+      unsigned hi = (unsigned)(k8 >> 32), lo = (unsigned)k8;
+      unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      bool c1 = hi == mh;
+      unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+      bool c2 = c1 && lo == ml;
+      const unsigned br = __reduce_min_sync(0xffffffffu, c2 ? r8 : 0x7fffffffu);
+      const int lr = (int)br - (int)row0;  // the CTA's candidate row is always one of its own live rows
       ll_store(&rows[par * G + blockIdx.x].v[lane], S[lane * PPITCH + lr], tag);
       if (blockIdx.x == 0) ll_store(&rowj[par].v[lane], S[lane * PPITCH + j], tag);  // row j lives in CTA 0
       if (lane == 0) {
         PanelHdr* h = &hdrs[par * G + blockIdx.x];
-        ll_store(&h->absval, bv, tag);
-        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(&h->row), "r"((unsigned)br), "r"(tag),
-                     "r"(0u), "r"(tag) : "memory");
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(&h->absval), "r"(ml), "r"(tag), "r"(mh), "r"(tag) : "memory");
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(&h->row), "r"(br), "r"(tag), "r"(0u), "r"(tag) : "memory");
       }
-      double wv = -2.0;
-      int wr = 0x7fffffff, wslot = 0;
+      if (dbg) t2 = clock64();
+      // every lane keeps the best of its slots, then the warp reduces
+      unsigned whi = 0, wlo = 0, wrow = 0x7fffffffu, wslot = 0;
       for (int q = lane; q < G; q += 32) {
         const PanelHdr* h = &hdrs[par * G + q];
-        double sv;
-        unsigned r0, t0, r1 = 0, t1;
+        unsigned a0, t0, a1, t1, r0, t2, r1 = 0, t3;
         bool ok;
         do {
-          ok = ll_load(&h->absval, tag, sv);
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(t0), "=r"(r1), "=r"(t1) : "l"(&h->row) : "memory");
-          ok = ok && t0 == tag && t1 == tag;
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a0), "=r"(t0), "=r"(a1), "=r"(t1) : "l"(&h->absval) : "memory");
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(t2), "=r"(r1), "=r"(t3) : "l"(&h->row) : "memory");
+          ok = t0 == tag && t1 == tag && t2 == tag && t3 == tag;
         } while (!ok);
-        int sr = (int)r0;
-        if (sv > wv || (sv == wv && sr < wr)) { wv = sv; wr = sr; wslot = q; }
+        bool better = a1 > whi || (a1 == whi && (a0 > wlo || (a0 == wlo && r0 < wrow)));
+        if (better) { whi = a1; wlo = a0; wrow = r0; wslot = (unsigned)q; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, wv, o);
-        int orow = __shfl_xor_sync(0xffffffffu, wr, o);
-        int oslot = __shfl_xor_sync(0xffffffffu, wslot, o);
-        if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wslot = oslot; }
-      }
+      mh = __reduce_max_sync(0xffffffffu, whi);
+      c1 = whi == mh;
+      ml = __reduce_max_sync(0xffffffffu, c1 ? wlo : 0u);
+      c2 = c1 && wlo == ml;
+      const unsigned wr = __reduce_min_sync(0xffffffffu, c2 ? wrow : 0x7fffffffu);
+      const unsigned ws = __reduce_min_sync(0xffffffffu, (c2 && wrow == wr) ? wslot : 0x7fffffffu);
+      if (dbg) t3 = clock64();
       double pv, rj;
-      while (!ll_load(&rows[par * G + wslot].v[lane], tag, pv)) {}
-      while (!ll_load(&rowj[par].v[lane], tag, rj)) {}
+      bool ok1, ok2;
+      do {  // both rows in flight together
+        ok1 = ll_load(&rows[par * G + ws].v[lane], tag, pv);
+        ok2 = ll_load(&rowj[par].v[lane], tag, rj);
+      } while (!(ok1 && ok2));
       s_prow[lane] = pv;
       s_rowj[lane] = rj;
-      if (lane == 0) s_piv = wr;
+      if (lane == 0) s_piv = (int)wr;
+      if (dbg) t4 = clock64();
     }
     __syncthreads();
+    if (dbg) t5 = clock64();
     const int p = s_piv;
     const double piv = s_prow[j];
     if (blockIdx.x == 0 && tid == 0) {
@@ -166,27 +178,55 @@ __global__ void __launch_bounds__(PR, 2) lla_dgetf2_panel_kernel(double* __restr
       if (piv == 0.0 && *info == 0) *info = (int)(off + j + 1);
     }
     // ---- 3. swap (only when the pivot is non-zero, as DGETF2 does), scale, rank-1 update
+    __shared__ long long s_dbg[4];
+    if (dbg && tid == PR - 1) s_dbg[0] = clock64();
     const bool swapped = (piv != 0.0) && (p != j);
-    if (live && grow == j) {
-      if (swapped)
-        for (int c = 0; c < PW; c++) S[c * PPITCH + tid] = s_prow[c];
-    } else if (live && grow > j) {
-      const bool isp = swapped && ((int)grow == p);  // this row receives the old row j
-      if (isp)
-        for (int c = 0; c < j; c++) S[c * PPITCH + tid] = s_rowj[c];
-      const double aj = isp ? s_rowj[j] : S[j * PPITCH + tid];
+    double rinv = 1.0;
+    if (piv != 0.0 && fabs(piv) >= sfmin) rinv = 1.0 / piv;
+    // The two rows of the interchange are rewritten by whole warps (lane c handles column c): a
+    // single thread walking 32 shared-memory cells would be the critical path of the column.
+    if (swapped && warp == 1 && blockIdx.x == 0) S[lane * PPITCH + j] = s_prow[lane];  // row j <- pivot row
+    if (swapped && warp == 2 && p >= row0 && p < row0 + PR) {                             // row p <- old row j, updated
+      const double ajp = s_rowj[j];
+      const double lp = (fabs(piv) >= sfmin) ? ajp * rinv : ajp / piv;
+      double val = s_rowj[lane];
+      if (lane == j) val = lp;
+      else if (lane > j) val = fma(-lp, s_prow[lane], val);
+      S[lane * PPITCH + (p - (int)row0)] = val;
+    }
+    if (dbg && tid == PR - 1) s_dbg[1] = clock64();
+    if (live && grow > j && !(swapped && (int)grow == p)) {
+      const double aj = S[j * PPITCH + tid];
       double l = aj;
-      if (piv != 0.0) l = (fabs(piv) >= sfmin) ? aj * (1.0 / piv) : aj / piv;
+      if (piv != 0.0) l = (fabs(piv) >= sfmin) ? aj * rinv : aj / piv;
       S[j * PPITCH + tid] = l;
-      // s_prow is row j of the panel after the interchange (a zero pivot implies p == j)
-      if (isp) {
-        for (int c = j + 1; c < PW; c++) S[c * PPITCH + tid] = fma(-l, s_prow[c], s_rowj[c]);
-      } else {
-#pragma unroll 4
-        for (int c = j + 1; c < PW; c++) S[c * PPITCH + tid] = fma(-l, s_prow[c], S[c * PPITCH + tid]);
+      // s_prow is row j of the panel after the interchange (a zero pivot implies p == j).
+      // Groups of 8 columns: all loads first, then the FMAs, then the stores (the compiler cannot
+      // prove that S and s_prow do not alias, so a plain loop would serialise on shared-memory latency)
+      for (int c8 = (j + 1) & ~7; c8 < PW; c8 += 8) {
+        double av[8], pv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { av[q] = S[(c8 + q) * PPITCH + tid]; pv[q] = s_prow[c8 + q]; }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (c8 + q > j) S[(c8 + q) * PPITCH + tid] = fma(-l, pv[q], av[q]);
       }
     }
+    if (dbg && tid == PR - 1) s_dbg[2] = clock64();
     __syncthreads();  // s_prow / s_rowj / s_piv / s_val are rewritten in the next column
+    if (dbg && tid == 0 && blockIdx.x == 0) {
+      long long t6 = clock64();
+      atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)(t1 - t0));
+      atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(t2 - t1));
+      atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(t3 - t2));
+      atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)(t4 - t3));
+      atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)(t5 - t4));
+      atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)(t6 - t5));
+      atomicAdd((unsigned long long*)&dbg[6], 1ull);
+      atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)(s_dbg[2] - s_dbg[1]));
+      atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(s_dbg[1] - s_dbg[0]));
+      atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(t6 - s_dbg[2]));
+    }
   }
 
   if (live) {
@@ -201,7 +241,7 @@ __global__ void __launch_bounds__(PR, 2) lla_dgetf2_panel_kernel(double* __restr
 // columns [0, ncols) of A except [skip0, skip1), 32 swaps at a time: warp 0 composes the chunk
 // into one permutation over the <= 64 touched rows, then the CTA gathers and scatters.
 constexpr int SW_CHUNK = 32;
-constexpr int SW_COLS = 16;
+constexpr int SW_COLS = 8;
 
 __global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) lla_dlaswp_kernel(double* __restrict__ A, int64_t lda, int64_t ncols,
                                                                        int64_t skip0, int64_t skip1, int64_t k1, int64_t k2,
@@ -317,7 +357,20 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   PanelRow* rj_ = L.rowj;
   unsigned epoch = g_panel_epoch++ & 0x03ffffffu;
   if (epoch == 0) epoch = g_panel_epoch++ & 0x03ffffffu;
-  void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &h_, &r_, &rj_, &epoch};
+  static long long* dbg = nullptr;
+  static bool dbg_checked = false;
+  if (!dbg_checked) {
+    dbg_checked = true;
+    if (getenv("LLACUDA_PANEL_DBG")) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
+  }
+  if (dbg && getenv("LLACUDA_PANEL_DBG_DUMP") && (g_panel_epoch % 64) == 0) {
+    long long h[16];
+    cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+    if (h[6]) fprintf(stderr, "  update detail: pre=%lld loop=%lld tail-sync=%lld\n", h[8] / h[6], h[7] / h[6], h[9] / h[6]);
+    if (h[6]) fprintf(stderr, "panel phases (cycles/step over %lld steps): cand=%lld pub=%lld poll=%lld fetch=%lld sync=%lld update=%lld\n",
+                      h[6], h[0] / h[6], h[1] / h[6], h[2] / h[6], h[3] / h[6], h[4] / h[6], h[5] / h[6]);
+  }
+  void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &h_, &r_, &rj_, &epoch, &dbg};
   LLA_CUDA(cudaLaunchCooperativeKernel((void*)lla_dgetf2_panel_kernel, dim3(G), dim3(PR), args, PANEL_SMEM, L.st));
   count_launch();
   // interchange the other columns of the swap window now: [swap_c0, j0) and [j0+w, swap_c1)
