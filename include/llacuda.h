@@ -74,6 +74,10 @@ int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, 
                            const double* A, int64_t lda, const double* B, int64_t ldb,
                            double beta, double* C, int64_t ldc, int tri);
 
+/* complex double (interleaved re,im); alpha2 / beta2 point at {re, im} on the host */
+int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
+                      const void* A, int64_t lda, const void* B, int64_t ldb,
+                      const double* beta2, void* C, int64_t ldc);
 /* factorisations and solves on device-resident column-major operands; ipiv_dev / info_dev are
  * DEVICE pointers (int32), written asynchronously on llacuda_stream() */
 int llacuda_dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv_dev, int* info_dev);
@@ -84,6 +88,12 @@ int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv
 int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, int* info_dev);
 int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const double* A, int64_t lda, double* B,
                        int64_t ldb);
+/* batched small solves (BASELINE configs[3]): `batch` independent n x n systems, n <= 32,
+ * nrhs <= 8; system i lives at A + i*strideA (column-major, lda = n) and B + i*strideB (ldb = n).
+ * X overwrites B; ipiv_dev (batch*n, may be NULL) and info_dev (batch) follow DGESV; A is only
+ * overwritten with the LU factors when keep_lu != 0 (LLA's solve discards them). */
+int llacuda_dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t strideA, int* ipiv_dev,
+                              double* B, int64_t strideB, int* info_dev, int keep_lu);
 /* out[c + r*ldout] = in[r + c*ldin]: the device-side replacement of LLA's
  * transpose-matrix-to/from-memory (reference src/foreign-memory.lisp:211-255) */
 int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out,
@@ -98,6 +108,12 @@ void llacuda_dgemm(const char* transa, const char* transb, const int* m, const i
                    const double* alpha, const double* a, const int* lda, const double* b,
                    const int* ldb, const double* beta, double* c, const int* ldc);
 
+void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+            const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
+            const void* beta, void* c, const int* ldc);
+void llacuda_zgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+                   const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
+                   const void* beta, void* c, const int* ldc);
 /* lu: src/linear-algebra.lisp:227-234 */
 void dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
 /* solve (lu): src/linear-algebra.lisp:269-276 */

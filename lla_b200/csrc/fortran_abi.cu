@@ -358,3 +358,75 @@ LLA_EXPORT int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* 
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   return dtranspose_dev(rows, cols, in, ldin, out, ldout, cx->stream);
 }
+
+// ------------------------------------------------------------------ ZGEMM
+static int zgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
+                      const cuDoubleComplex* a, int64_t lda, const cuDoubleComplex* b, int64_t ldb,
+                      cuDoubleComplex beta, cuDoubleComplex* c, int64_t ldc) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  if (m == 0 || n == 0) return 0;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  const bool need_ab = (k > 0 && !(alpha.x == 0.0 && alpha.y == 0.0));
+  const bool need_c = !(beta.x == 0.0 && beta.y == 0.0);
+  Staged sa, sb, sc;
+  int64_t ar = oa ? k : m, ac = oa ? m : k;
+  int64_t br = ob ? n : k, bc = ob ? k : n;
+  if (need_ab) {
+    LLA_TRY(stage_alloc(sa, ar, ac, sizeof(cuDoubleComplex)));
+    LLA_TRY(stage_alloc(sb, br, bc, sizeof(cuDoubleComplex)));
+    LLA_TRY(stage_upload(sa, a, lda, st));
+    LLA_TRY(stage_upload(sb, b, ldb, st));
+  }
+  LLA_TRY(stage_alloc(sc, m, n, sizeof(cuDoubleComplex)));
+  if (need_c) LLA_TRY(stage_upload(sc, c, ldc, st));
+  tm.mark(1);
+  LLA_TRY(zgemm_dev(oa, ob, m, n, k, alpha, sa.ptr<cuDoubleComplex>(), sa.ld, sb.ptr<cuDoubleComplex>(), sb.ld, beta,
+                    sc.ptr<cuDoubleComplex>(), sc.ld, TRI_FULL, st));
+  tm.mark(2);
+  LLA_TRY(stage_download(sc, c, ldc, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call sites: mm src/linear-algebra.lisp:50-54, gemm! src/blas.lisp:56-63 (complex-double arrays) */
+LLA_EXPORT void zgemm_(const char* transa, const char* transb, const int* m_, const int* n_, const int* k_,
+                       const void* alpha, const void* a, const int* lda_, const void* b, const int* ldb_,
+                       const void* beta, void* c, const int* ldc_) {
+  int oa = opcode(*transa), ob = opcode(*transb);
+  int64_t m = *m_, n = *n_, k = *k_, lda = *lda_, ldb = *ldb_, ldc = *ldc_;
+  int64_t nrowa = oa ? k : m, nrowb = ob ? n : k;
+  int bad = 0;
+  if (oa < 0) bad = 1;
+  else if (ob < 0) bad = 2;
+  else if (m < 0) bad = 3;
+  else if (n < 0) bad = 4;
+  else if (k < 0) bad = 5;
+  else if (lda < (nrowa > 1 ? nrowa : 1)) bad = 8;
+  else if (ldb < (nrowb > 1 ? nrowb : 1)) bad = 10;
+  else if (ldc < (m > 1 ? m : 1)) bad = 13;
+  if (bad) { blas_arg_error("ZGEMM ", bad); return; }
+  int r = zgemm_host(oa, ob, m, n, k, *(const cuDoubleComplex*)alpha, (const cuDoubleComplex*)a, lda,
+                     (const cuDoubleComplex*)b, ldb, *(const cuDoubleComplex*)beta, (cuDoubleComplex*)c, ldc);
+  if (r != 0) fprintf(stderr, " ** llacuda: zgemm_ failed: %s\n", llacuda_last_error());
+}
+LLA_EXPORT void llacuda_zgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+                              const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
+                              const void* beta, void* c, const int* ldc) {
+  zgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+LLA_EXPORT int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
+                                 const void* A, int64_t lda, const void* B, int64_t ldb, const double* beta2,
+                                 void* C, int64_t ldc) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  int oa = opcode(opa), ob = opcode(opb);
+  if (oa < 0 || ob < 0 || m < 0 || n < 0 || k < 0) return LLACUDA_ERR_BAD_ARG;
+  return zgemm_dev(oa, ob, m, n, k, make_cuDoubleComplex(alpha2[0], alpha2[1]), (const cuDoubleComplex*)A, lda,
+                   (const cuDoubleComplex*)B, ldb, make_cuDoubleComplex(beta2[0], beta2[1]), (cuDoubleComplex*)C, ldc,
+                   TRI_FULL, cx->stream);
+}

@@ -58,6 +58,9 @@ constexpr size_t PANEL_SMEM = (size_t)PW * PPITCH * sizeof(double);
 // owns row t; warp 0 runs the cross-CTA exchange of every column.  These kernels are bound by
 // instruction latency (a handful of warps per SM), so the per-column instruction count is what
 // is being minimised here -- no unrolled register-array selects, real loops with dynamic bounds.
+// The rank-1 update rounds the product and the subtraction separately, exactly as DGETF2/DGER do,
+// so a matrix that fits one leaf (n <= 32) is factored bit-identically to the reference algorithm
+// and exact ties between pivot candidates resolve the same way.
 __global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
                                                                  int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
                                                                  PanelHdr* __restrict__ hdrs, PanelRow* __restrict__ rows,
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restr
       const double lp = (fabs(piv) >= sfmin) ? ajp * rinv : ajp / piv;
       double val = s_rowj[lane];
       if (lane == j) val = lp;
-      else if (lane > j) val = fma(-lp, s_prow[lane], val);
+      else if (lane > j) val = __dsub_rn(val, __dmul_rn(lp, s_prow[lane]));
       S[lane * PPITCH + (p - (int)row0)] = val;
     }
     if (dbg && tid == PR - 1) s_dbg[1] = clock64();
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restr
         for (int q = 0; q < 8; q++) { av[q] = S[(c8 + q) * PPITCH + tid]; pv[q] = s_prow[c8 + q]; }
 #pragma unroll
         for (int q = 0; q < 8; q++)
-          if (c8 + q > j) S[(c8 + q) * PPITCH + tid] = fma(-l, pv[q], av[q]);
+          if (c8 + q > j) S[(c8 + q) * PPITCH + tid] = __dsub_rn(av[q], __dmul_rn(l, pv[q]));
       }
     }
     if (dbg && tid == PR - 1) s_dbg[2] = clock64();

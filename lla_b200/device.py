@@ -75,3 +75,16 @@ def dpotrs(uplo, n, nrhs, A, lda, B, ldb):
 def dtranspose(rows, cols, src, ldin, dst, ldout):
     f = _sig("llacuda_dtranspose_dev", [_i64, _i64, _vp, _i64, _vp, _i64])
     _lib.check(f(rows, cols, src, ldin, dst, ldout), "dtranspose_dev")
+
+
+def zgemm(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+    f = _sig("llacuda_zgemm_dev", [_chr, _chr, _i64, _i64, _i64, ctypes.POINTER(_dbl), _vp, _i64, _vp, _i64,
+                                   ctypes.POINTER(_dbl), _vp, _i64])
+    al = (_dbl * 2)(alpha.real, alpha.imag)
+    be = (_dbl * 2)(beta.real, beta.imag)
+    _lib.check(f(opa.encode(), opb.encode(), m, n, k, al, A, lda, B, ldb, be, C, ldc), "zgemm_dev")
+
+
+def dgesv_batched(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu=0):
+    f = _sig("llacuda_dgesv_batched_dev", [ctypes.c_int, ctypes.c_int, _i64, _vp, _i64, _ip, _vp, _i64, _ip, ctypes.c_int])
+    _lib.check(f(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu), "dgesv_batched_dev")

@@ -77,6 +77,21 @@ def test_lu_vs_oracle(shape):
     assert np.max(np.abs(f.lu - r1.lu)) <= scale
 
 
+def test_lu_small_is_bit_identical_to_reference_algorithm():
+    """n <= 32 is a single DGETF2 leaf: same operations in the same order => identical bits."""
+    rng = np.random.default_rng(12)
+    for n in (2, 5, 17, 32):
+        for _ in range(10):
+            a = rng.uniform(-10, 10, (n, n))
+            f, r = L.lu(a), O.lu(a, O.netlib())
+            assert np.array_equal(f.ipiv_internal, r.ipiv_internal)
+            assert np.array_equal(f.lu, r.lu)
+        b = rng.integers(-2, 3, (n, n)).astype(np.float64)
+        f, r = L.lu(b), O.lu(b, O.netlib())
+        assert np.array_equal(f.ipiv_internal, r.ipiv_internal)
+        assert np.array_equal(np.nan_to_num(f.lu, nan=1e300), np.nan_to_num(r.lu, nan=1e300))
+
+
 def test_lu_ties_and_zero_columns():
     """exact ties (first index must win), a zero column (INFO = its index, factorisation goes on)."""
     a = np.ones((40, 40))

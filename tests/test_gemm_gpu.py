@@ -111,3 +111,50 @@ def test_mm_linearity_large():
     rhs = L.mm(a1, b) + L.mm(a2, b)
     assert np.all(np.abs(lhs - rhs) <= 2 * gemm_tol(np.abs(a1) + np.abs(a2), b, n))
     assert np.array_equal(L.mm(a1, np.eye(n)), a1)
+
+
+# ------------------------------------------------------------------ complex double (ZGEMM)
+EPSZ = np.finfo(np.float64).eps
+
+
+def crand(rng, *shape):
+    return rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)
+
+
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (5, 7, 3), (64, 64, 64), (70, 130, 33), (129, 65, 100), (200, 31, 257)])
+def test_zgemm_vs_oracle(ta, tb, m, n, k):
+    """gemm! on complex-double arrays: a transposed operand is CONJUGATE-transposed (src/blas.lisp:57-58)."""
+    rng = np.random.default_rng(m * 100 + n * 10 + k)
+    a = crand(rng, *((k, m) if ta else (m, k)))
+    b = crand(rng, *((n, k) if tb else (k, n)))
+    c = crand(rng, m, n)
+    for alpha, beta in ((1.0 + 0j, 0j), (0.7 - 0.2j, 1.3 + 0.5j), (0j, 0.5 + 0.1j)):
+        want = O.gemm(alpha, a, b, beta, c.copy(), O.openblas(), transpose_a=ta, transpose_b=tb)
+        got = L.gemm(alpha, a, b, beta, c.copy(), transpose_a=ta, transpose_b=tb)
+        opa = a.conj().T if ta else a
+        opb = b.conj().T if tb else b
+        tol = 2 * gemm_tol(np.abs(opa), np.abs(opb), k, abs(alpha)) + 8 * EPSZ * abs(beta) * np.abs(c)
+        assert np.all(np.abs(got - want) <= tol)
+
+
+def test_zmm_mixed_types_and_identity():
+    rng = np.random.default_rng(8)
+    a = crand(rng, 90, 40)
+    b = rng.uniform(-1, 1, (40, 70))              # real * complex -> complex-double (LOGIOR of the codes)
+    got = L.mm(a, b)
+    assert got.dtype == np.complex128
+    assert np.allclose(got, a @ b, atol=40 * 8 * EPSZ)
+    assert np.array_equal(L.mm(a, np.eye(40)), a)
+
+
+def test_zgemm_large_property():
+    """n = 1500: conj-transpose identity (A B)^H = B^H A^H through the two transposed code paths."""
+    rng = np.random.default_rng(4)
+    n = 1500
+    a, b = crand(rng, n, n), crand(rng, n, n)
+    ab = L.mm(a, b)
+    c = np.zeros((n, n), dtype=np.complex128)
+    bhah = L.gemm(1.0, b, a, 0.0, c, transpose_a=True, transpose_b=True)
+    assert np.all(np.abs(ab.conj().T - bhah) <= 4 * gemm_tol(np.abs(a), np.abs(b), n).T)
