@@ -1,0 +1,44 @@
+"""world_size-2 gloo tests (CPU) of the block-cyclic layer: ownership arithmetic and the SUMMA
+driver's panel schedule, with a torch stand-in for the local GEMM (the product path uses the DMMA
+kernel; see tests/test_dist_gpu.py for the GPU leg)."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = """
+import sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from lla_b200 import dist as LD
+dist.init_process_group("gloo")
+world, rank = dist.get_world_size(), dist.get_rank()
+for (P, Q) in ((1, 2), (2, 1)):
+    grid = LD.make_grid(P, Q)
+    m, n, k, nb = 8 * P, 12 * Q, 4 * P * Q, 2
+    torch.manual_seed(0)
+    A = torch.rand((k, m), dtype=torch.float64)      # column-major images
+    B = torch.rand((n, k), dtype=torch.float64)
+    la, lb, lc = LD.BlockCyclic(m, k, nb, grid), LD.BlockCyclic(k, n, nb, grid), LD.BlockCyclic(m, n, nb, grid)
+    A_loc, B_loc = la.scatter_from_global(A), lb.scatter_from_global(B)
+    assert torch.equal(la.gather_to_global(A_loc), A)          # scatter/gather round trip
+    C_loc = torch.zeros((n // Q, m // P), dtype=torch.float64)
+    for look in (True, False):
+        LD.summa(grid, m, n, k, nb, A_loc, B_loc, C_loc, local_gemm=LD.torch_gemm, lookahead=look)
+        C = lc.gather_to_global(C_loc)
+        want = (A.t() @ B.t()).t()
+        assert torch.allclose(C, want, atol=1e-12), (P, Q, look)
+assert LD.choose_grid(8) == (2, 4) and LD.choose_grid(4) == (2, 2) and LD.choose_grid(2) == (1, 2)
+dist.destroy_process_group()
+"""
+
+
+def test_summa_block_cyclic_two_ranks(tmp_path):
+    script = tmp_path / "summa.py"
+    script.write_text(SCRIPT.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
