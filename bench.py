@@ -398,7 +398,7 @@ def main():
                 "ops_frac_of_fp64_tensor_roof": {k: f[k] * args.steps / (g["t_ms"][k] * 1e-3) / 1e12 / peak for k in f},
                 "parity": {"solve_scaled_residual": g["solve_resid"], "bound": 10, "info": g["info"]},
                 "clocks": g["clocks"], "e2e": g["e2e"], "gpu_launches": g["launches"],
-                "roofline": {"kernel": "dgemm_kernel<128,128,16> (DMMA m8n8k4), the mm launch of the step",
+                "roofline": {"kernel": "lla_dgemm_kernel<128,64,16,...> (DMMA m8n8k4, two CTAs/SM), the mm launch of the step; algorithmic flop = 2 n^3",
                              "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                              "traffic": traffic,
                              "peak_source": "in-run llacuda_probe_fp64_peak DMMA loop; MEASURED_PEAKS.json has no FP64 figure "

@@ -1,0 +1,115 @@
+;;; -*- Mode:Lisp; Syntax:ANSI-Common-Lisp; Coding:utf-8 -*-
+;;;
+;;; llacuda-glue.lisp -- the Lisp side of the llacuda drop-in for tpapp/lla.
+;;;
+;;; WRITTEN BLIND: the build image has no Common Lisp implementation (sbcl/ecl/ccl/clisp are all
+;;; absent) and none of LLA's Lisp dependencies, so nothing in this file has been compiled or run.
+;;; It is kept tiny and mechanical on purpose.  What IS tested is the C ABI these forms bind to
+;;; (tests/ drive the very same symbols through ctypes with LLA's argument lists, see
+;;; lla_b200/lla.py, which mirrors LLA's layers L7..L3 one to one).
+;;;
+;;; Load AFTER the stock LLA system:   (asdf:load-system "lla") (load "llacuda-glue.lisp")
+;;;
+;;; Option A of INTEGRATION.md needs none of this: put "libllacuda.so" first in
+;;;   (defvar cl-user::*lla-configuration* '(:libraries ("libllacuda.so" "liblapack.so" "libblas.so")))
+;;; and the unchanged `foreign-funcall "dgemm_"` of src/fortran-call.lisp:428-439 resolves into it.
+;;; This file is Option B: explicit re-pointing of the name generator plus the device-resident
+;;; extras, touching the subsystems BASELINE.json names.
+
+(in-package #:lla)
+
+;;;; --- libraries.lisp: load the device library next to the host BLAS/LAPACK -------------------
+;;; reference: src/libraries.lisp:10-12 loads (query-configuration :libraries ...) at load time.
+
+(defparameter *llacuda-library* (query-configuration :llacuda-library "libllacuda.so"))
+(defparameter *llacuda-enabled* nil
+  "T once libllacuda.so is loaded and llacuda_init() found an sm_100 device.")
+(defparameter *llacuda-min-dimension* (query-configuration :llacuda-min-n 256)
+  "Below this matrix order the PCIe round trip costs more than host BLAS; calls stay on the host.")
+
+(defun llacuda-load ()
+  (cffi:load-foreign-library *llacuda-library*)
+  (setf *llacuda-enabled*
+        (zerop (cffi:foreign-funcall "llacuda_init" :int)))
+  (unless *llacuda-enabled*
+    (warn "llacuda: ~A" (cffi:foreign-funcall "llacuda_last_error" :string)))
+  *llacuda-enabled*)
+
+;;;; --- fortran-call.lisp: re-point the name generator for the hot-path routines ----------------
+;;; reference: src/fortran-call.lisp:405-416 builds "dgemm_" from type letter + name; the ECASE of
+;;; :428-439 is generated at macroexpansion time, so LLA's linear-algebra.lisp and blas.lisp must be
+;;; recompiled after this redefinition (asdf:load-system "lla" :force t), or use Option A.
+
+(defparameter *llacuda-routines*
+  '(("D" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs"))
+    ("Z" . ("gemm")))
+  "Routines libllacuda.so exports as llacuda_<letter><name> with the Fortran signature.")
+
+(defun llacuda-routine-p (letter name)
+  (member name (cdr (assoc letter *llacuda-routines* :test #'string-equal))
+          :test #'string-equal))
+
+(defun blas-lapack-function-name (type name)
+  "As the reference (src/fortran-call.lisp:405-416), but emits the llacuda_ entry point for the
+routines the device library implements.  Same argument list, same void return, same INFO cell."
+  (let+ (((real-name &optional (complex-name name)) (ensure-list name))
+         (letter (switch (type)
+                   (+single+ "S")
+                   (+double+ "D")
+                   (+complex-single+ "C")
+                   (+complex-double+ "Z")))
+         (name (if (complex? type) complex-name real-name)))
+    (if (llacuda-routine-p letter name)
+        (format nil "llacuda_~(~A~A~)" letter name)
+        (format nil "~(~A~A_~)" letter name))))
+
+;;;; --- conditions: device failures are NOT LAPACK INFO codes -----------------------------------
+;;; reference: src/fortran-call.lisp:336-347 maps INFO<0 to lapack-invalid-argument.  libllacuda
+;;; reports CUDA failures as INFO <= -10000 plus a message; surface them as their own condition.
+
+(define-condition llacuda-device-error (error)
+  ((info :initarg :info :reader info)
+   (message :initarg :message :reader message))
+  (:report (lambda (c stream)
+             (format stream "llacuda device failure (INFO=~A): ~A" (info c) (message c)))))
+
+(defun llacuda-check-info (info)
+  (when (<= info -10000)
+    (error 'llacuda-device-error
+           :info info
+           :message (cffi:foreign-funcall "llacuda_last_error" :string))))
+
+;;;; --- foreign-memory.lisp / pinned-array.lisp: pinned staging for large operands ---------------
+;;; reference: src/pinned-array.lisp:105-109 (WITH-WORK-AREA = cffi:with-foreign-pointer) and
+;;; :135-141 (sb-sys:with-pinned-objects).  Lisp heap vectors are pageable; for operands above a
+;;; few MiB a page-locked work area lets the library DMA at PCIe rate.  The library detects
+;;; page-locked pointers itself, so this is purely an allocation policy.
+
+(defmacro with-llacuda-work-area ((pointer size) &body body)
+  "Like WITH-WORK-AREA but the SIZE bytes are page-locked host memory (llacuda_host_alloc)."
+  (with-unique-names (holder)
+    `(cffi:with-foreign-object (,holder :pointer)
+       (let ((rc (cffi:foreign-funcall "llacuda_host_alloc" :pointer ,holder :size ,size :int)))
+         (unless (zerop rc) (llacuda-check-info rc)))
+       (let ((,pointer (cffi:mem-ref ,holder :pointer)))
+         (unwind-protect (progn ,@body)
+           (cffi:foreign-funcall "llacuda_host_free" :pointer ,pointer :int))))))
+
+;;;; --- factorizations.lisp / linear-algebra.lisp: device-resident factors (SURVEY 8f rank 1) ----
+;;; A LU or CHOLESKY object may keep its factors on the device so that (solve factorization b)
+;;; does not re-upload (and, for LU, re-transpose: src/linear-algebra.lisp:264-276) n^2 numbers on
+;;; every call.  The handle is a device pointer from llacuda_malloc; the *_dev entry points of
+;;; include/llacuda.h take it directly (column-major, 64-bit dimensions).
+
+(defclass device-lu (lu)
+  ((device-lu :initarg :device-lu :reader device-lu :documentation "device pointer, column-major LU")
+   (device-ipiv :initarg :device-ipiv :reader device-ipiv))
+  (:documentation "LU factorization whose factors also live in HBM."))
+
+(defun llacuda-device-free (pointer)
+  (cffi:foreign-funcall "llacuda_free" :pointer pointer :int))
+
+;;; (solve device-lu b) => llacuda_dgetrs_dev('N', n, nrhs, dev-lu, n, dev-ipiv, dev-b, n), with b
+;;; staged through llacuda_memcpy_h2d / llacuda_dtranspose_dev instead of TRANSPOSE-MATRIX-TO-MEMORY
+;;; (src/foreign-memory.lisp:211-230).  The method bodies follow the host methods line by line and
+;;; are left to the maintainer who can run them; the C side is complete and tested.
