@@ -74,6 +74,11 @@ int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, 
                            const double* A, int64_t lda, const double* B, int64_t ldb,
                            double beta, double* C, int64_t ldc, int tri);
 
+/* single precision on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulation in TMEM), TMA-fed:
+ * A, B 16-byte aligned with lda, ldb multiples of 4 */
+int llacuda_sgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, float alpha,
+                      const float* A, int64_t lda, const float* B, int64_t ldb,
+                      float beta, float* C, int64_t ldc);
 /* complex double (interleaved re,im); alpha2 / beta2 point at {re, im} on the host */
 int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
                       const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -108,6 +113,12 @@ void llacuda_dgemm(const char* transa, const char* transb, const int* m, const i
                    const double* alpha, const double* a, const int* lda, const double* b,
                    const int* ldb, const double* beta, double* c, const int* ldc);
 
+void sgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+            const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
+            const float* beta, float* c, const int* ldc);
+void llacuda_sgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+                   const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
+                   const float* beta, float* c, const int* ldc);
 void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
             const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
             const void* beta, void* c, const int* ldc);

@@ -430,3 +430,60 @@ LLA_EXPORT int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64
                    (const cuDoubleComplex*)B, ldb, make_cuDoubleComplex(beta2[0], beta2[1]), (cuDoubleComplex*)C, ldc,
                    TRI_FULL, cx->stream);
 }
+
+// ------------------------------------------------------------------ SGEMM
+static int sgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, float alpha, const float* a, int64_t lda,
+                      const float* b, int64_t ldb, float beta, float* c, int64_t ldc) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  if (m == 0 || n == 0) return 0;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  const bool need_ab = (k > 0 && alpha != 0.0f);
+  Staged sa, sb, sc;
+  int64_t ar = oa ? k : m, ac = oa ? m : k;
+  int64_t br = ob ? n : k, bc = ob ? k : n;
+  if (need_ab) {
+    LLA_TRY(stage_alloc(sa, ar, ac, sizeof(float)));
+    LLA_TRY(stage_alloc(sb, br, bc, sizeof(float)));
+    LLA_TRY(stage_upload(sa, a, lda, st));
+    LLA_TRY(stage_upload(sb, b, ldb, st));
+  }
+  LLA_TRY(stage_alloc(sc, m, n, sizeof(float)));
+  if (beta != 0.0f) LLA_TRY(stage_upload(sc, c, ldc, st));
+  tm.mark(1);
+  LLA_TRY(sgemm_dev(oa, ob, m, n, k, alpha, sa.ptr<float>(), sa.ld, sb.ptr<float>(), sb.ld, beta, sc.ptr<float>(), sc.ld, st));
+  tm.mark(2);
+  LLA_TRY(stage_download(sc, c, ldc, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call sites: mm src/linear-algebra.lisp:50-54, gemm! src/blas.lisp:56-63 (single-float arrays) */
+LLA_EXPORT void sgemm_(const char* transa, const char* transb, const int* m_, const int* n_, const int* k_,
+                       const float* alpha, const float* a, const int* lda_, const float* b, const int* ldb_,
+                       const float* beta, float* c, const int* ldc_) {
+  int oa = opcode(*transa), ob = opcode(*transb);
+  int64_t m = *m_, n = *n_, k = *k_, lda = *lda_, ldb = *ldb_, ldc = *ldc_;
+  int64_t nrowa = oa ? k : m, nrowb = ob ? n : k;
+  int bad = 0;
+  if (oa < 0) bad = 1;
+  else if (ob < 0) bad = 2;
+  else if (m < 0) bad = 3;
+  else if (n < 0) bad = 4;
+  else if (k < 0) bad = 5;
+  else if (lda < (nrowa > 1 ? nrowa : 1)) bad = 8;
+  else if (ldb < (nrowb > 1 ? nrowb : 1)) bad = 10;
+  else if (ldc < (m > 1 ? m : 1)) bad = 13;
+  if (bad) { blas_arg_error("SGEMM ", bad); return; }
+  int r = sgemm_host(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc);
+  if (r != 0) fprintf(stderr, " ** llacuda: sgemm_ failed: %s\n", llacuda_last_error());
+}
+LLA_EXPORT void llacuda_sgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+                              const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
+                              const float* beta, float* c, const int* ldc) {
+  sgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}

@@ -81,6 +81,10 @@ int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex
               const cuDoubleComplex* A, int64_t lda, const cuDoubleComplex* B, int64_t ldb,
               cuDoubleComplex beta, cuDoubleComplex* C, int64_t ldc, int tri, cudaStream_t st);
 
+// SGEMM on tcgen05 / TMEM / TMA (gemm_f32.cu); lda, ldb multiples of 4, operands 16-byte aligned
+int sgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st);
+
 // ------------------------------------------------------------------ TRSM (trsm_f64.cu), left side only
 // solves op(T) X = alpha B in place; T is m x m triangular, B is m x n
 int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n,

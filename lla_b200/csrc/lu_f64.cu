@@ -35,7 +35,9 @@ constexpr int PR = 128;    // rows (= threads) per CTA
 // expected tag in every word holds a consistent record and no fence or atomic is on the critical
 // path.  tag = (launch epoch << 6) | (column + 1) is unique per launch and column.
 struct __align__(16) LLDouble { unsigned lo, tag0, hi, tag1; };
-struct __align__(32) PanelHdr { LLDouble absval; unsigned row, tag2, pad, tag3; };
+// one header per 256-byte chunk: all G CTAs poll all G headers every column, and consecutive 256-byte
+// chunks map to different L2 slices, so the polling traffic is spread instead of hammering one slice
+struct __align__(256) PanelHdr { LLDouble absval; unsigned row, tag2, pad, tag3; };
 struct PanelRow { LLDouble v[PW]; };
 
 __device__ __forceinline__ void ll_store(LLDouble* p, double x, unsigned tag) {

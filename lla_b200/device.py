@@ -88,3 +88,11 @@ def zgemm(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
 def dgesv_batched(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu=0):
     f = _sig("llacuda_dgesv_batched_dev", [ctypes.c_int, ctypes.c_int, _i64, _vp, _i64, _ip, _vp, _i64, _ip, ctypes.c_int])
     _lib.check(f(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu), "dgesv_batched_dev")
+
+
+_flt = ctypes.c_float
+
+
+def sgemm(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+    f = _sig("llacuda_sgemm_dev", [_chr, _chr, _i64, _i64, _i64, _flt, _vp, _i64, _vp, _i64, _flt, _vp, _i64])
+    _lib.check(f(opa.encode(), opb.encode(), m, n, k, alpha, A, lda, B, ldb, beta, C, ldc), "sgemm_dev")

@@ -158,3 +158,49 @@ def test_zgemm_large_property():
     c = np.zeros((n, n), dtype=np.complex128)
     bhah = L.gemm(1.0, b, a, 0.0, c, transpose_a=True, transpose_b=True)
     assert np.all(np.abs(ab.conj().T - bhah) <= 4 * gemm_tol(np.abs(a), np.abs(b), n).T)
+
+
+# ------------------------------------------------------------------ single precision (tcgen05, 3xTF32)
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def sgemm_tol(opa, opb, K, scale=1.0):
+    """k * eps32 * ||a_i|| ||b_j|| with k = 16 + 4 sqrt(K): the 3xTF32 split drops terms of relative
+    size 2^-21 per product (8 eps32) on top of the FP32 accumulation error."""
+    ra = np.linalg.norm(opa.astype(np.float64), axis=1)[:, None]
+    cb = np.linalg.norm(opb.astype(np.float64), axis=0)[None, :]
+    return (16 + 4 * np.sqrt(max(K, 1))) * EPS32 * scale * ra * cb + 1e-30
+
+
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (5, 7, 3), (128, 128, 32), (128, 128, 64), (130, 70, 33), (257, 129, 100), (64, 300, 257)])
+def test_sgemm_vs_oracle(ta, tb, m, n, k):
+    rng = np.random.default_rng(m * 100 + n * 10 + k)
+    a = rng.uniform(-1, 1, (k, m) if ta else (m, k)).astype(np.float32)
+    b = rng.uniform(-1, 1, (n, k) if tb else (k, n)).astype(np.float32)
+    c = rng.uniform(-1, 1, (m, n)).astype(np.float32)
+    for alpha, beta in ((1.0, 0.0), (0.7, 1.3), (0.0, 0.5)):
+        got = L.gemm(alpha, a, b, beta, c.copy(), transpose_a=ta, transpose_b=tb)
+        assert got.dtype == np.float32
+        opa = (a.T if ta else a).astype(np.float64)
+        opb = (b.T if tb else b).astype(np.float64)
+        want = alpha * (opa @ opb) + beta * c.astype(np.float64)
+        tol = sgemm_tol(opa, opb, k, abs(alpha)) + 4 * EPS32 * (abs(beta) * np.abs(c) + np.abs(want))
+        assert np.all(np.abs(got.astype(np.float64) - want) <= tol), np.max(np.abs(got - want) / tol)
+
+
+def test_smm_accuracy_is_fp32_grade_not_tf32():
+    """plain TF32 would be wrong at the 1e-3 level; the 3xTF32 split with chunked accumulation must be at
+    the 1e-6 level even for all-positive data (the tensor core's truncating FP32 accumulation alone
+    gave 2.3e-5 here; with 128-deep TMEM chunks the residual bias is ~128 * 2^-24 * 0.4 = 3e-6)."""
+    rng = np.random.default_rng(6)
+    n = 1024
+    a = rng.uniform(0, 1, (n, n)).astype(np.float32)
+    b = rng.uniform(0, 1, (n, n)).astype(np.float32)
+    got = L.mm(a, b).astype(np.float64)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    rel = np.max(np.abs(got - want) / np.abs(want))
+    assert rel < 4e-6, rel
+    ref32 = O.mm(a, b, O.openblas()).astype(np.float64)        # host SGEMM for comparison
+    assert rel <= 4 * np.max(np.abs(ref32 - want) / np.abs(want)) + 1e-6
