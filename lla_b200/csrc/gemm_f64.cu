@@ -136,7 +136,10 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) lla_dgemm_ke
   // CTAs resident at any time cover a compact block of C and share their A / B panels through L2
   constexpr int GROUP_M = 16;
   const int tiles_m = (int)((p.M + BM - 1) / BM), tiles_n = (int)((p.N + BN - 1) / BN);
-  const int pid = blockIdx.x;
+  if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
+  // persistent form: with gridDim.x == number of tiles this loop runs once; a smaller grid (SM
+  // reservation for a concurrent panel stream) makes every CTA walk several tiles
+  for (int pid = blockIdx.x; pid < tiles_m * tiles_n; pid += gridDim.x) {
   const int group = pid / (GROUP_M * tiles_n);
   const int first_m = group * GROUP_M;
   const int gsz = (tiles_m - first_m) < GROUP_M ? (tiles_m - first_m) : GROUP_M;
@@ -144,9 +147,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) lla_dgemm_ke
   const int tn = (pid % (GROUP_M * tiles_n)) / gsz;
   const int64_t m0 = (int64_t)tm * BM;
   const int64_t n0 = (int64_t)tn * BN;
-  if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
-  if (p.tri == TRI_UPPER && m0 > n0 + BN - 1) return;  // tile entirely below the diagonal
-  if (p.tri == TRI_LOWER && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
+  if (p.tri == TRI_UPPER && m0 > n0 + BN - 1) continue;  // tile entirely below the diagonal
+  if (p.tri == TRI_LOWER && n0 > m0 + BM - 1) continue;  // tile entirely above the diagonal
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -226,6 +228,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) lla_dgemm_ke
       }
     }
   }
+  __syncthreads();  // the next tile's prologue overwrites the shared-memory ring
+  }  // persistent tile loop
 }
 
 // C = beta*C when k == 0 or alpha == 0 (netlib quick return path)
@@ -242,7 +246,7 @@ __global__ void lla_dscale_c_kernel(int64_t M, int64_t N, double* C, int64_t ldc
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, bool AL16, int MINB>
-static int launch_cfg(const DgemmParams& p, cudaStream_t st) {
+static int launch_cfg(const DgemmParams& p, cudaStream_t st, int64_t max_ctas = 0) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   using TSA = TileShape<BM, BK, !TA>;
   using TSB = TileShape<BN, BK, TB>;
@@ -254,6 +258,7 @@ static int launch_cfg(const DgemmParams& p, cudaStream_t st) {
     configured = true;
   }
   int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  if (max_ctas > 0 && tiles > max_ctas) tiles = max_ctas;
   dim3 grid((unsigned)tiles);
   kern<<<grid, NT, SMEM, st>>>(p);
   count_launch();
@@ -264,6 +269,8 @@ static int launch_cfg(const DgemmParams& p, cudaStream_t st) {
 template <bool TA, bool TB, bool AL16>
 static int launch_shape(const DgemmParams& p, cudaStream_t st, int sm_count, int hint) {
   if (hint == GEMM_INPLACE_B) return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
+  if (hint == GEMM_RESERVE_SMS)  // one CTA per SM on all but 8 SMs, which stay free for the panel stream
+    return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st, sm_count - 8);
   int64_t big_tiles = ((p.M + 127) / 128) * ((p.N + 127) / 128);
   if (p.tri != TRI_FULL) big_tiles = big_tiles / 2 + 1;
   if (big_tiles >= 2 * (int64_t)sm_count) {

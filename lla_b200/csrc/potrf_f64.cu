@@ -15,6 +15,8 @@
 #include "tri128.cuh"
 #include "../../include/llacuda.h"
 
+#include <cstdlib>
+
 namespace llacuda {
 
 // One CTA factors an r x r (r <= 128) diagonal block held in shared memory as L = U^T, writes U
@@ -66,9 +68,13 @@ static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, double* uin
 // update of step k-1 is split into (a) the block row that panel k needs and (b) everything below.
 static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* info, cudaStream_t s1) {
   Context* c = ctx();
-  const int64_t NB = 512;
+  // measured on B200 (profiles/r01_cholesky_nb.txt): n = 16384: NB 256 / 512 / 1024 / 2048 -> 101 / 78.5 / 68.6 / 68.4 ms;
+  // n = 8192: 17.3 / 15.2 / 15.9 / 18.4 ms
+  static int64_t NB_env = -1;
+  if (NB_env < 0) { const char* e = getenv("LLACUDA_CHOL_NB"); NB_env = e ? atoi(e) : 0; }
+  const int64_t NB = NB_env > 0 ? NB_env : (n >= 12288 ? 1024 : 512);
   if (n <= 2 * NB) return potrf_rec(n, A, lda, 0, uinv, info, s1);
-  cudaStream_t s2 = c->aux;
+  cudaStream_t s2 = getenv("LLACUDA_NO_LOOKAHEAD") ? s1 : c->aux;
   cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
   LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
@@ -95,7 +101,7 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     const int64_t n3 = n2 - kb_next;
     if (n3 > 0)
       LLA_TRY(dgemm_dev(1, 0, n3, n3, kb, -1.0, Arow + kb_next * lda, lda, Arow + kb_next * lda, lda, 1.0,
-                        Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info));
+                        Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info, getenv("LLACUDA_CHOL_RESERVE") ? GEMM_RESERVE_SMS : GEMM_AUTO));
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   return 0;
