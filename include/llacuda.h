@@ -59,6 +59,7 @@ int  llacuda_host_free(void* p);
 int  llacuda_memcpy_h2d(void* dst, const void* src, size_t bytes);
 int  llacuda_memcpy_d2h(void* dst, const void* src, size_t bytes);
 int  llacuda_memset(void* dst, int byte, size_t bytes);
+int  llacuda_trim(void);                        /* release the cached device staging buffers */
 
 /* FP64 roof probes: sustained TFLOP/s of a register-resident DMMA (kind 0) or DFMA (kind 1)
  * loop on every SM; the roofline denominator bench.py reports against (MEASURED_PEAKS.json

@@ -4,6 +4,7 @@
 // foreign-funcall), so the device state is a lazily-initialised process global guarded by a
 // mutex (SURVEY.md section 8b "Threading / reentrancy").
 #include "internal.h"
+#include "staging.h"
 #include "../../include/llacuda.h"
 
 #include <atomic>
@@ -188,6 +189,7 @@ int llacuda_host_alloc(void** p, size_t bytes) {
   LLA_CUDA(cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault));
   return 0;
 }
+int llacuda_trim(void) { return pool_trim(); }
 int llacuda_host_free(void* p) { LLA_CUDA(cudaFreeHost(p)); return 0; }
 int llacuda_memcpy_h2d(void* dst, const void* src, size_t bytes) {
   Context* c = ctx();

@@ -32,6 +32,10 @@ static void blas_arg_error(const char* routine, int pos) {
 }
 
 // ------------------------------------------------------------------ GEMM
+// C = alpha op(A) op(B) + beta C with HOST operands.  Large products are pipelined over column
+// chunks of op(B) / C on three streams: while the DMMA GEMM of chunk j runs, chunk j+1 of B (and of C
+// when beta != 0) is uploaded and chunk j-1 of C is downloaded, so only the upload of A and the
+// first / last chunk transfers are exposed.
 static int dgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, double alpha, const double* a,
                       int64_t lda, const double* b, int64_t ldb, double beta, double* c, int64_t ldc) {
   Context* cx = ctx();
@@ -47,19 +51,65 @@ static int dgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, double al
   if (need_ab) {
     LLA_TRY(stage_alloc(sa, ar, ac, sizeof(double)));
     LLA_TRY(stage_alloc(sb, br, bc, sizeof(double)));
-    LLA_TRY(stage_upload(sa, a, lda, st));
-    LLA_TRY(stage_upload(sb, b, ldb, st));
   }
   LLA_TRY(stage_alloc(sc, m, n, sizeof(double)));
-  if (beta != 0.0) LLA_TRY(stage_upload(sc, c, ldc, st));
+  const double work = 2.0 * (double)m * (double)n * (double)(k > 0 ? k : 1);
+  const int chunks = (need_ab && !ob && work > 4e10 && n >= 2048) ? 8 : 1;   // op(B) = B: its columns are C's columns
+  if (chunks == 1) {
+    if (need_ab) {
+      LLA_TRY(stage_upload(sa, a, lda, st));
+      LLA_TRY(stage_upload(sb, b, ldb, st));
+    }
+    if (beta != 0.0) LLA_TRY(stage_upload(sc, c, ldc, st));
+    tm.mark(1);
+    LLA_TRY(dgemm_dev(oa, ob, m, n, k, alpha, sa.ptr<double>(), sa.ld, sb.ptr<double>(), sb.ld, beta,
+                      sc.ptr<double>(), sc.ld, TRI_FULL, st));
+    tm.mark(2);
+    LLA_TRY(stage_download(sc, c, ldc, st));
+    tm.mark(3);
+    LLA_CUDA(cudaStreamSynchronize(st));
+    tm.finish();
+    return 0;
+  }
+  cudaStream_t sh = cx->h2d, sd = cx->d2h;
+  cudaEvent_t ev_in[8], ev_done[8], ev_start;
+  LLA_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  for (int j = 0; j < chunks; j++) {
+    LLA_CUDA(cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming));
+    LLA_CUDA(cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming));
+  }
+  LLA_CUDA(cudaEventRecord(ev_start, st));
+  LLA_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
+  LLA_CUDA(cudaStreamWaitEvent(sd, ev_start, 0));
+  LLA_TRY(stage_upload(sa, a, lda, sh));
+  const int64_t step = ((n + chunks - 1) / chunks + 63) / 64 * 64;
+  for (int j = 0; j < chunks; j++) {
+    const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
+    if (c0 >= n) { LLA_CUDA(cudaEventRecord(ev_in[j], sh)); continue; }
+    LLA_TRY(stage_upload_cols(sb, b, ldb, c0, c1, sh));
+    if (beta != 0.0) LLA_TRY(stage_upload_cols(sc, c, ldc, c0, c1, sh));
+    LLA_CUDA(cudaEventRecord(ev_in[j], sh));
+  }
   tm.mark(1);
-  LLA_TRY(dgemm_dev(oa, ob, m, n, k, alpha, sa.ptr<double>(), sa.ld, sb.ptr<double>(), sb.ld, beta,
-                    sc.ptr<double>(), sc.ld, TRI_FULL, st));
+  for (int j = 0; j < chunks; j++) {
+    const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
+    if (c0 >= n) break;
+    LLA_CUDA(cudaStreamWaitEvent(st, ev_in[j], 0));
+    LLA_TRY(dgemm_dev(oa, ob, m, c1 - c0, k, alpha, sa.ptr<double>(), sa.ld, sb.ptr<double>() + c0 * sb.ld, sb.ld, beta,
+                      sc.ptr<double>() + c0 * sc.ld, sc.ld, TRI_FULL, st));
+    LLA_CUDA(cudaEventRecord(ev_done[j], st));
+    LLA_CUDA(cudaStreamWaitEvent(sd, ev_done[j], 0));
+    LLA_TRY(stage_download_cols(sc, c, ldc, c0, c1, sd));
+  }
   tm.mark(2);
-  LLA_TRY(stage_download(sc, c, ldc, st));
+  LLA_CUDA(cudaEventRecord(ev_start, sd));
+  LLA_CUDA(cudaStreamWaitEvent(st, ev_start, 0));
   tm.mark(3);
   LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_CUDA(cudaStreamSynchronize(sd));
   tm.finish();
+  cudaEventDestroy(ev_start);
+  for (int j = 0; j < chunks; j++) { cudaEventDestroy(ev_in[j]); cudaEventDestroy(ev_done[j]); }
   return 0;
 }
 
@@ -101,7 +151,7 @@ static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, int* ipiv, 
   PhaseTimer tm(st);
   tm.mark(0);
   Staged sa;
-  DevBuf piv, inf;
+  PoolBuf piv, inf;
   int64_t mn = m < n ? m : n;
   LLA_TRY(stage_alloc(sa, m, n, sizeof(double)));
   LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(mn)));
@@ -139,7 +189,7 @@ static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t
   PhaseTimer tm(st);
   tm.mark(0);
   Staged sa, sb;
-  DevBuf piv;
+  PoolBuf piv;
   LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
   LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
   LLA_TRY(piv.alloc(sizeof(int) * (size_t)n));
@@ -180,7 +230,7 @@ static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, int* ipiv
   PhaseTimer tm(st);
   tm.mark(0);
   Staged sa, sb;
-  DevBuf piv, inf;
+  PoolBuf piv, inf;
   LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
   LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
   LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(n)));
@@ -224,7 +274,7 @@ static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, int* info)
   PhaseTimer tm(st);
   tm.mark(0);
   Staged sa;
-  DevBuf inf;
+  PoolBuf inf;
   LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
   LLA_TRY(inf.alloc(sizeof(int)));
   LLA_TRY(stage_upload(sa, a, lda, st));

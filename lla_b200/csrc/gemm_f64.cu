@@ -269,8 +269,8 @@ static int launch_cfg(const DgemmParams& p, cudaStream_t st, int64_t max_ctas = 
 template <bool TA, bool TB, bool AL16>
 static int launch_shape(const DgemmParams& p, cudaStream_t st, int sm_count, int hint) {
   if (hint == GEMM_INPLACE_B) return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
-  if (hint == GEMM_RESERVE_SMS)  // one CTA per SM on all but 8 SMs, which stay free for the panel stream
-    return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st, sm_count - 8);
+  if (hint >= GEMM_RESERVE_SMS)  // one CTA per SM on all but (hint - GEMM_RESERVE_SMS + 8) SMs, which stay free for the panel stream
+    return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st, sm_count - (8 + hint - GEMM_RESERVE_SMS));
   int64_t big_tiles = ((p.M + 127) / 128) * ((p.N + 127) / 128);
   if (p.tri != TRI_FULL) big_tiles = big_tiles / 2 + 1;
   if (big_tiles >= 2 * (int64_t)sm_count) {

@@ -76,8 +76,8 @@ int dgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, double alpha,
               const int* abort_flag = nullptr, int hint = 0);
 // hint 1: m <= 128 and C aliases B (in-place product): force a single row of 128-row tiles so
 // that every column slab of B/C is read and then written by exactly one CTA.
-// hint 2: persistent 128x128 tiles on (SM count - 8) CTAs, so that the kernels of a concurrent
-// high-priority panel stream always find a free SM (look-ahead in the blocked factorisations).
+// hint 2 + r: persistent 128x128 tiles on (SM count - 8 - r) CTAs, one per SM, so that the kernels of
+// a concurrent high-priority panel stream always find free SMs (look-ahead in the blocked factorisations).
 enum GemmHint { GEMM_AUTO = 0, GEMM_INPLACE_B = 1, GEMM_RESERVE_SMS = 2 };
 int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
               const cuDoubleComplex* A, int64_t lda, const cuDoubleComplex* B, int64_t ldb,

@@ -423,7 +423,7 @@ static int lu_rec(const LuCtx& L, int64_t j0, int64_t m, int64_t n) {
 }
 
 // columns [c0, c1) right of panel (k, kb): interchanges, U12 = L11^-1 A12, A22 -= A21 U12
-static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st) {
+static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st, int hint = GEMM_AUTO) {
   if (c1 <= c0) return 0;
   const int64_t nc = c1 - c0;
   double* A11 = L.A + k + k * L.lda;
@@ -431,7 +431,8 @@ static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int
   LLA_TRY(dlaswp_dev(nc, L.A + c0 * L.lda, L.lda, k, k + kb, L.ipiv, true, st));
   LLA_TRY(dtrsm_left_inv_dev(false, 0, kb, nc, A11, L.lda, L.linv + (k / IB) * IB * IB, A12, L.lda, st));
   if (L.M > k + kb)
-    LLA_TRY(dgemm_dev(0, 0, L.M - k - kb, nc, kb, -1.0, A11 + kb, L.lda, A12, L.lda, 1.0, A12 + kb, L.lda, TRI_FULL, st));
+    LLA_TRY(dgemm_dev(0, 0, L.M - k - kb, nc, kb, -1.0, A11 + kb, L.lda, A12, L.lda, 1.0, A12 + kb, L.lda, TRI_FULL, st,
+                      nullptr, hint));
   return 0;
 }
 
@@ -441,7 +442,9 @@ static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int
 // stream, since nothing depends on them until the end.
 static int lu_blocked(LuCtx L) {
   Context* c = ctx();
-  const int64_t NB = 512;
+  static int64_t NB_env = -1;
+  if (NB_env < 0) { const char* e = getenv("LLACUDA_LU_NB"); NB_env = e ? atoi(e) : 0; }
+  const int64_t NB = NB_env > 0 ? NB_env : 512;
   const int64_t mn = L.M < L.N ? L.M : L.N;
   if (mn <= 2 * NB) {
     L.swap_c0 = 0; L.swap_c1 = L.N;
@@ -475,7 +478,12 @@ static int lu_blocked(LuCtx L) {
     LLA_TRY(lu_update_cols(L, k, kb, c0, c1, s1));
     LLA_CUDA(cudaEventRecord(ev_a, s1));
     LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
-    LLA_TRY(lu_update_cols(L, k, kb, c1, L.N, s1));
+    // the rest of the update runs as a persistent GEMM that leaves `reserve` SMs to the panel stream:
+    // the factorisation is bound by the panel chain, so the chain gets SMs of its own
+    static int reserve = -1;
+    if (reserve < 0) { const char* e = getenv("LLACUDA_LU_RESERVE"); reserve = e ? atoi(e) : 0; }  // measured: no gain on B200 (profiles/r01_lu_tuning.txt), off by default
+    const bool overlap = (c1 < L.N) && (k + kb < mn);
+    LLA_TRY(lu_update_cols(L, k, kb, c1, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
     LLA_CUDA(cudaEventRecord(ev_b, s1));
     have_b = true;
   }

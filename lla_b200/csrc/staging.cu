@@ -2,7 +2,63 @@
 #include "staging.h"
 #include "../../include/llacuda.h"
 
+#include <mutex>
+#include <vector>
+
 namespace llacuda {
+
+namespace {
+struct Block { void* p; size_t bytes; bool used; };
+std::mutex g_pool_mu;
+std::vector<Block> g_pool;
+}  // namespace
+
+int PoolBuf::alloc(size_t n) {
+  if (n == 0) n = 16;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); i++)
+      if (!g_pool[i].used && g_pool[i].bytes >= n && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+    if (best >= 0 && g_pool[best].bytes <= 2 * n + (size_t(1) << 20)) {
+      g_pool[best].used = true;
+      p = g_pool[best].p;
+      bytes = g_pool[best].bytes;
+      return 0;
+    }
+  }
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n);
+  if (e != cudaSuccess) {   // out of memory: drop the cached blocks and retry once
+    pool_trim();
+    e = cudaMalloc(&q, n);
+    if (e != cudaSuccess) return record_cuda_error(e, __FILE__, __LINE__);
+  }
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool.push_back({q, n, true});
+  p = q;
+  bytes = n;
+  return 0;
+}
+
+PoolBuf::~PoolBuf() {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (auto& b : g_pool)
+    if (b.p == p) { b.used = false; break; }
+}
+
+int pool_trim() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  cudaDeviceSynchronize();
+  std::vector<Block> keep;
+  for (auto& b : g_pool) {
+    if (b.used) keep.push_back(b);
+    else cudaFree(b.p);
+  }
+  g_pool.swap(keep);
+  return 0;
+}
 
 int stage_alloc(Staged& s, int64_t rows, int64_t cols, size_t es) {
   s.rows = rows;
@@ -24,6 +80,22 @@ int stage_download(const Staged& s, void* host, int64_t ldh, cudaStream_t st) {
   if (s.rows <= 0 || s.cols <= 0) return 0;
   LLA_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * s.es, s.buf.p, (size_t)s.ld * s.es, (size_t)s.rows * s.es,
                              (size_t)s.cols, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int stage_upload_cols(Staged& s, const void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st) {
+  if (s.rows <= 0 || c1 <= c0) return 0;
+  LLA_CUDA(cudaMemcpy2DAsync((char*)s.buf.p + (size_t)c0 * s.ld * s.es, (size_t)s.ld * s.es,
+                             (const char*)host + (size_t)c0 * ldh * s.es, (size_t)ldh * s.es, (size_t)s.rows * s.es,
+                             (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+int stage_download_cols(const Staged& s, void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st) {
+  if (s.rows <= 0 || c1 <= c0) return 0;
+  LLA_CUDA(cudaMemcpy2DAsync((char*)host + (size_t)c0 * ldh * s.es, (size_t)ldh * s.es,
+                             (const char*)s.buf.p + (size_t)c0 * s.ld * s.es, (size_t)s.ld * s.es, (size_t)s.rows * s.es,
+                             (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 

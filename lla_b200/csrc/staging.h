@@ -10,8 +10,18 @@
 
 namespace llacuda {
 
+// Device staging buffers come from a grow-only pool (cudaMalloc / cudaFree of multi-GiB blocks cost
+// tens of milliseconds each and cudaFree synchronises the device); llacuda_trim() releases it.
+struct PoolBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n);
+  ~PoolBuf();
+};
+int pool_trim();
+
 struct Staged {
-  DevBuf buf;
+  PoolBuf buf;
   int64_t ld = 0;
   int64_t rows = 0, cols = 0;
   size_t es = 0;
@@ -22,6 +32,9 @@ int stage_alloc(Staged& s, int64_t rows, int64_t cols, size_t es);
 int stage_upload(Staged& s, const void* host, int64_t ldh, cudaStream_t st);
 // upload only the part of the matrix selected by tri (0 all, 1 upper incl. diagonal, 2 lower)
 int stage_download(const Staged& s, void* host, int64_t ldh, cudaStream_t st);
+// column range [c0, c1) only
+int stage_upload_cols(Staged& s, const void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st);
+int stage_download_cols(const Staged& s, void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st);
 
 // wall-clock phases of one host-pointer call, written to ctx()->last_ms
 struct PhaseTimer {
