@@ -204,3 +204,20 @@ def test_smm_accuracy_is_fp32_grade_not_tf32():
     assert rel < 4e-6, rel
     ref32 = O.mm(a, b, O.openblas()).astype(np.float64)        # host SGEMM for comparison
     assert rel <= 4 * np.max(np.abs(ref32 - want) / np.abs(want)) + 1e-6
+
+
+# ------------------------------------------------------------------ degenerate shapes (netlib quick returns)
+def test_gemm_degenerate_shapes():
+    rng = np.random.default_rng(3)
+    c = rng.uniform(-1, 1, (4, 5))
+    # k = 0: C = beta * C, A and B are never read
+    got = L.gemm(1.0, np.zeros((4, 0)), np.zeros((0, 5)), 0.5, c.copy(), k=0, lda=1, ldb=5)
+    assert np.allclose(got, 0.5 * c, rtol=0, atol=1e-16)
+    # m = 0 / n = 0: nothing happens
+    e = np.zeros((0, 5))
+    assert L.gemm(1.0, np.zeros((0, 3)), np.zeros((3, 5)), 0.0, e, lda=3).shape == (0, 5)
+    # vectors through mm: (1 x n) and (n x 1) results
+    a = rng.uniform(-1, 1, (1, 200))
+    b = rng.uniform(-1, 1, (200, 1))
+    assert np.allclose(L.mm(a, b), a @ b, atol=1e-13)
+    assert np.allclose(L.mm(b, a), b @ a, atol=1e-13)
