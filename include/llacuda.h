@@ -51,6 +51,8 @@ int  llacuda_set_stream(void* cuda_stream);    /* adopt a caller-owned stream (N
 int  llacuda_reset_stream(void);               /* back to the library's own stream */
 int  llacuda_synchronize(void);
 unsigned long long llacuda_launch_count(void); /* llacuda kernels launched so far by this process */
+void llacuda_trace_enable(int on);             /* diagnostics: event trace of the blocked drivers (also LLACUDA_TRACE=1) */
+void llacuda_trace_dump(void);                 /* print "t_ms stream label a b" per mark to stderr, then clear */
 int  llacuda_last_timing(float* ms4);          /* last host-pointer call: h2d, compute, d2h, total */
 int  llacuda_malloc(void** p, size_t bytes);
 int  llacuda_free(void* p);

@@ -8,6 +8,7 @@
 #include "../../include/llacuda.h"
 
 #include <atomic>
+#include <vector>
 #include <mutex>
 #include <cstdio>
 #include <cstring>
@@ -98,6 +99,22 @@ void* Arena::take(size_t bytes) {
   return base + a;
 }
 
+// ---- event trace (diagnostics only)
+struct TraceRec { cudaEvent_t ev; cudaStream_t st; const char* label; long long a, b; };
+static std::vector<TraceRec> g_trace;
+static int g_trace_on = -1;
+bool trace_on() {
+  if (g_trace_on < 0) g_trace_on = getenv("LLACUDA_TRACE") ? 1 : 0;
+  return g_trace_on == 1;
+}
+void trace_mark(cudaStream_t st, const char* label, long long a, long long b) {
+  if (!trace_on()) return;
+  TraceRec r{nullptr, st, label, a, b};
+  if (cudaEventCreate(&r.ev) != cudaSuccess) return;
+  cudaEventRecord(r.ev, st);
+  g_trace.push_back(r);
+}
+
 int DevBuf::alloc(size_t n) {
   if (n == 0) n = 16;
   cudaError_t e = cudaMalloc(&p, n);
@@ -168,6 +185,20 @@ int llacuda_synchronize(void) {
   LLA_CUDA(cudaStreamSynchronize(c->stream));
   LLA_CUDA(cudaStreamSynchronize(c->aux));
   return 0;
+}
+
+void llacuda_trace_enable(int on) { g_trace_on = on ? 1 : 0; }
+// prints "t_ms stream label a b" for every mark since the last dump, relative to the first mark
+void llacuda_trace_dump(void) {
+  cudaDeviceSynchronize();
+  for (size_t i = 0; i < g_trace.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+    fprintf(stderr, "TRACE %10.3f s%03x %-14s %lld %lld\n", ms, (unsigned)(((uintptr_t)g_trace[i].st >> 4) & 0xfff),
+            g_trace[i].label, g_trace[i].a, g_trace[i].b);
+  }
+  for (auto& r : g_trace) cudaEventDestroy(r.ev);
+  g_trace.clear();
 }
 
 int llacuda_last_timing(float* ms4) {

@@ -206,25 +206,50 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) lla_dgemm_ke
 
   // ---- epilogue: C = alpha*acc + beta*C straight from the fragment registers.
   const double alpha = p.alpha, beta = p.beta;
-  const bool diag_tile = p.tri != TRI_FULL;
+  // only tiles that straddle the diagonal pay for the per-element triangle test (tile-uniform branch): behind
+  // it the loads of C cannot be batched, which cost the SYRK-shaped updates 12 % on B200 when every tile took it
+  const bool diag_tile = (p.tri == TRI_UPPER && m0 + BM - 1 > n0) || (p.tri == TRI_LOWER && n0 + BN - 1 > m0);
+  const bool interior = m0 + BM <= p.M && n0 + BN <= p.N;
+  if (!diag_tile && interior) {
 #pragma unroll
-  for (int j = 0; j < NI; j++) {
+    for (int j = 0; j < NI; j++) {
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      int64_t gn = n0 + wn0 + j * 8 + 2 * lc + e;
-      if (gn >= p.N) continue;
-      double* ccol = p.C + gn * p.ldc;
+      for (int e = 0; e < 2; e++) {
+        double* ccol = p.C + (n0 + wn0 + j * 8 + 2 * lc + e) * p.ldc + m0 + wm0 + lr;
+        if (beta != 0.0) {
+          double cv[MI];
 #pragma unroll
-      for (int i = 0; i < MI; i++) {
-        int64_t gm = m0 + wm0 + i * 8 + lr;
-        if (gm >= p.M) continue;
-        if (diag_tile) {
+          for (int i = 0; i < MI; i++) cv[i] = ccol[i * 8];
+#pragma unroll
+          for (int i = 0; i < MI; i++) {
+            double v = alpha * acc[i][j][e];
+            v += beta * cv[i];  // same expression as the edge path (identical contraction / rounding)
+            ccol[i * 8] = v;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < MI; i++) ccol[i * 8] = alpha * acc[i][j][e];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int64_t gn = n0 + wn0 + j * 8 + 2 * lc + e;
+        if (gn >= p.N) continue;
+        double* ccol = p.C + gn * p.ldc;
+#pragma unroll
+        for (int i = 0; i < MI; i++) {
+          int64_t gm = m0 + wm0 + i * 8 + lr;
+          if (gm >= p.M) continue;
           if (p.tri == TRI_UPPER && gm > gn) continue;
           if (p.tri == TRI_LOWER && gm < gn) continue;
+          double v = alpha * acc[i][j][e];
+          if (beta != 0.0) v += beta * ccol[gm];
+          ccol[gm] = v;
         }
-        double v = alpha * acc[i][j][e];
-        if (beta != 0.0) v += beta * ccol[gm];
-        ccol[gm] = v;
       }
     }
   }

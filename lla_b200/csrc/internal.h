@@ -59,6 +59,11 @@ struct Arena {
 // number of llacuda kernels launched by this process (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 
+// Event trace of the blocked drivers (diagnostics; LLACUDA_TRACE=1): trace_mark records a timing event
+// on `st`; llacuda_trace_dump() prints every mark's time relative to the first one.
+void trace_mark(cudaStream_t st, const char* label, long long a = 0, long long b = 0);
+bool trace_on();
+
 // device scratch allocations that live for one call
 struct DevBuf {
   void* p = nullptr;

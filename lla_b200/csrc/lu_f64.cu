@@ -35,38 +35,62 @@ constexpr int PR = 128;    // rows (= threads) per CTA
 // expected tag in every word holds a consistent record and no fence or atomic is on the critical
 // path.  tag = (launch epoch << 6) | (column + 1) is unique per launch and column.
 struct __align__(16) LLDouble { unsigned lo, tag0, hi, tag1; };
-// one header per 256-byte chunk: all G CTAs poll all G headers every column, and consecutive 256-byte
-// chunks map to different L2 slices, so the polling traffic is spread instead of hammering one slice
-struct __align__(256) PanelHdr { LLDouble absval; unsigned row, tag2, pad, tag3; };
-struct PanelRow { LLDouble v[PW]; };
+// One key header per CTA and column parity, 256 bytes apart: all G CTAs poll all G headers every column, and
+// consecutive 256-byte chunks map to different L2 slices, so the polling traffic is spread.  (An all-to-all
+// push into per-reader inboxes was measured slower on B200: tools/mb/xchg.cu, 4615 vs 3710 cycles at G = 128.)
+// The header is the CTA's best |a_ij| as an order-preserving 64-bit key; ties between CTAs resolve to the
+// lowest CTA (= lowest row: each CTA reports its first maximum), so the row index travels with the row.
+// Candidate rows are pulled: only the winner's row is read (v[PW] = reciprocal of its pivot value).
+struct __align__(256) PanelHdr { LLDouble key; };
+
+struct PanelRow { LLDouble v[PW + 1]; unsigned row, tag2, pad, tag3; };
 
 __device__ __forceinline__ void ll_store(LLDouble* p, double x, unsigned tag) {
   unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
   asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
+__device__ __forceinline__ void ll_store_u(void* p, unsigned a, unsigned b, unsigned tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(tag), "r"(b), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ll_load_u(const void* p, unsigned tag, unsigned& a, unsigned& b) {
+  unsigned t0, t1;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a), "=r"(t0), "=r"(b), "=r"(t1) : "l"(p) : "memory");
+  return t0 == tag && t1 == tag;
+}
 __device__ __forceinline__ bool ll_load(const LLDouble* p, unsigned tag, double& x) {
-  unsigned a, b, c, d;
-  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  unsigned a, c;
+  bool ok = ll_load_u(p, tag, a, c);
   x = __hiloint2double((int)c, (int)a);
-  return b == tag && d == tag;
+  return ok;
 }
 
 constexpr int PPITCH = PR + 1;                       // shared-memory pitch of one panel column
 constexpr size_t PANEL_SMEM = (size_t)PW * PPITCH * sizeof(double);
 
+// multiplier of DGETF2: reciprocal scaling when |pivot| >= sfmin, division otherwise, nothing for a zero pivot
+__device__ __forceinline__ double lu_multiplier(double a, double piv, double rinv) {
+  if (piv == 0.0) return a;
+  return (fabs(piv) >= DBL_MIN) ? a * rinv : a / piv;
+}
+
 // A: top-left of the panel (diagonal element of the full matrix), m rows x w columns.
 // ipiv/info are indexed / valued relative to the full matrix through `off` (global row of the top).
-// The CTA's 256 x 32 slice of the panel lives in shared memory (column c at S + c*PPITCH), thread t
-// owns row t; warp 0 runs the cross-CTA exchange of every column.  These kernels are bound by
-// instruction latency (a handful of warps per SM), so the per-column instruction count is what
-// is being minimised here -- no unrolled register-array selects, real loops with dynamic bounds.
-// The rank-1 update rounds the product and the subtraction separately, exactly as DGETF2/DGER do,
-// so a matrix that fits one leaf (n <= 32) is factored bit-identically to the reference algorithm
-// and exact ties between pivot candidates resolve the same way.
+// The CTA's 128 x 32 slice of the panel lives in shared memory (column c at S + c*PPITCH), thread t
+// owns row t; warp 0 runs the cross-CTA exchange of every column.
+//
+// The column loop is software-pipelined around the exchange, which is the critical path (two L2 round
+// trips per column): once pivot q = j-1 is known every thread applies it to column j ONLY, the arg-max
+// of column j starts at once, and each warp stages the fully updated copy of its candidate row (one
+// row, lane = column).  The rank-1 update of the remaining columns j+1.. runs while the candidates
+// travel through L2.  The arithmetic is unchanged: the update rounds the product and the subtraction
+// separately, exactly as DGETF2/DGER do, so a matrix that fits one leaf (n <= 32) is factored
+// bit-identically to the reference algorithm and exact ties between pivot candidates resolve the same way.
+template <bool DBG>
 __global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
                                                                  int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
                                                                  PanelHdr* __restrict__ hdrs, PanelRow* __restrict__ rows,
-                                                                 PanelRow* __restrict__ rowj, unsigned epoch, long long* dbg) {
+                                                                 PanelRow* __restrict__ rowj, unsigned epoch,
+                                                                 unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double S[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -85,154 +109,188 @@ __global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restr
     for (int c = 0; c < 8; c++) S[(c8 + c) * PPITCH + tid] = v[c];
   }
 
-  __shared__ unsigned long long s_key[PR / 32];
-  __shared__ int s_row[PR / 32];
-  __shared__ double s_prow[PW];
-  __shared__ double s_rowj[PW];
+  constexpr int NW = PR / 32;
+  __shared__ unsigned long long s_key[NW];
+  __shared__ int s_row[NW];
+  __shared__ double s_cand[NW][PW + 1];  // each warp's candidate row, updated through the pending pivot; [PW] = 1 / its pivot value
+  __shared__ double s_rowj_out[PW];      // CTA 0: row j, updated through the pending pivot
+  __shared__ double s_prow[2][PW];       // pivot row of column j in s_prow[j & 1]
+  __shared__ double s_rowq[PW];          // the row that sat at position j before the interchange
+  __shared__ double s_rinv;
   __shared__ int s_piv;
   __syncthreads();
 
-  const double sfmin = DBL_MIN;
+  double lmul = 0.0;  // this row's multiplier for the pending pivot
 
 #pragma unroll 1
-  for (int j = 0; j < nsteps; j++) {
+  for (int j = 0; j <= nsteps; j++) {
+    const int q = j - 1;  // pending pivot: known, applied to nothing yet
+    bool upd = false;
+    long long tk[7];
+    if (DBG) tk[0] = clock64();
+    const double* prow = s_prow[q & 1];
+    double xj = 0.0;      // this row's element of column j, after the pending update
+    if (q >= 0) {
+      const int p = s_piv;
+      const double piv = prow[q];
+      const double rinv = s_rinv;
+      if (blockIdx.x == 0 && tid == 0) {
+        ipiv[off + q] = (int)(off + p + 1);
+        if (piv == 0.0 && *info == 0) *info = (int)(off + q + 1);
+      }
+      // ---- interchange (only when the pivot is non-zero, as DGETF2 does): whole warps rewrite the two
+      // rows (lane = column); row p is rewritten by the warp that owns it, so __syncwarp orders it
+      if (piv != 0.0 && p != q) {
+        const int pl = p - (int)row0;
+        if (pl >= 0 && pl < PR && warp == (pl >> 5)) { S[lane * PPITCH + pl] = s_rowq[lane]; __syncwarp(); }
+        if (blockIdx.x == 0 && warp == NW - 1) S[lane * PPITCH + q] = prow[lane];  // final: nobody reads row q again
+      }
+      // ---- multiplier, and the update of column j only
+      if (live && grow > q) {
+        upd = true;
+        lmul = lu_multiplier(S[q * PPITCH + tid], piv, rinv);
+        S[q * PPITCH + tid] = lmul;
+        if (j < w) {
+          xj = __dsub_rn(S[j * PPITCH + tid], __dmul_rn(lmul, prow[j]));
+          S[j * PPITCH + tid] = xj;
+        }
+      }
+      __syncwarp();
+    } else if (live) {
+      xj = S[tid];
+    }
+    if (j < nsteps) {
+      // ---- candidate of this warp: first row (>= j) with the largest |a[j]|; NaN only wins as row j.
+      // The magnitude becomes an order-preserving 64-bit key (0 = no number here) so that the
+      // arg-max is three 32-bit REDUX operations instead of five rounds of 64-bit shuffles.
+      unsigned long long key = 0ull;
+      unsigned r = 0x7fffffffu;
+      if (live && grow >= j) {
+        double x = fabs(xj);
+        bool isn = (x != x);
+        if (grow == j && isn) x = INFINITY;  // IDAMAX: dmax = NaN, nothing compares greater
+        if (x == x) key = (unsigned long long)__double_as_longlong(x) + 1ull;
+        r = (unsigned)grow;
+      }
+      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const bool c1 = hi == mh;
+      const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+      const bool c2 = c1 && lo == ml;
+      const unsigned rm = __reduce_min_sync(0xffffffffu, c2 ? r : 0x7fffffffu);
+      if (lane == 0) { s_key[warp] = ((unsigned long long)mh << 32) | ml; s_row[warp] = (int)rm; }
+      if (rm != 0x7fffffffu) {  // warp-uniform: stage the candidate row as it will be after the pending update
+        const int lr = (int)rm - (int)row0;
+        const double cv = __shfl_sync(0xffffffffu, xj, lr & 31);
+        double v = S[lane * PPITCH + lr];
+        if (q >= 0 && lane > j) v = __dsub_rn(v, __dmul_rn(S[q * PPITCH + lr], prow[lane]));
+        s_cand[warp][lane] = v;
+        if (lane == 0) s_cand[warp][PW] = 1.0 / cv;  // the division overlaps the barrier and the CTA reduction
+      }
+      if (blockIdx.x == 0 && warp == 0) {  // row j lives in CTA 0, warp 0
+        double v = S[lane * PPITCH + j];
+        if (q >= 0 && lane > j) v = __dsub_rn(v, __dmul_rn(S[q * PPITCH + j], prow[lane]));
+        s_rowj_out[lane] = v;
+      }
+    }
+    if (DBG) tk[1] = clock64();
+    __syncthreads();
     const int par = j & 1;
     const unsigned tag = (epoch << 6) | (unsigned)(j + 1);
-    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
-    if (dbg) t0 = clock64();
-    // ---- 1. candidate of this warp: first row (>= j) with the largest |a[j]|; NaN only wins as row j.
-    // The magnitude is turned into an order-preserving 64-bit key (0 = no number here) so that the
-    // arg-max is three 32-bit REDUX operations instead of five rounds of 64-bit shuffles.
-    unsigned long long key = 0ull;
-    unsigned r = 0x7fffffffu;
-    if (live && grow >= j) {
-      double x = fabs(S[j * PPITCH + tid]);
-      bool isn = (x != x);
-      if (grow == j && isn) x = INFINITY;  // IDAMAX: dmax = NaN, nothing compares greater
-      if (x == x) key = (unsigned long long)__double_as_longlong(x) + 1ull;
-      r = (unsigned)grow;
-    }
-    {
-      unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-      unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-      bool c1 = hi == mh;
-      unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
-      bool c2 = c1 && lo == ml;
-      unsigned rm = __reduce_min_sync(0xffffffffu, c2 ? r : 0x7fffffffu);
-      if (lane == 0) { s_key[warp] = ((unsigned long long)mh << 32) | ml; s_row[warp] = (int)rm; }
-    }
-    __syncthreads();
-    if (dbg) t1 = clock64();
-    // ---- 2. warp 0: CTA candidate, publish, wait for every CTA, pick the winner, fetch its row
-    if (warp == 0) {
-      unsigned long long k8 = (lane < PR / 32) ? s_key[lane] : 0ull;
-      unsigned r8 = (lane < PR / 32) ? (unsigned)s_row[lane] : 0x7fffffffu;
+    PanelHdr* hd = hdrs + (size_t)par * G;
+    if (warp == 0 && j < nsteps) {
+      // ---- CTA candidate: publish the key, then the row
+      unsigned long long k8 = (lane < NW) ? s_key[lane] : 0ull;
+      unsigned r8 = (lane < NW) ? (unsigned)s_row[lane] : 0x7fffffffu;
       unsigned hi = (unsigned)(k8 >> 32), lo = (unsigned)k8;
       unsigned mh = __reduce_max_sync(0xffffffffu, hi);
       bool c1 = hi == mh;
       unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
       bool c2 = c1 && lo == ml;
       const unsigned br = __reduce_min_sync(0xffffffffu, c2 ? r8 : 0x7fffffffu);
-      const int lr = (int)br - (int)row0;  // the CTA's candidate row is always one of its own live rows
-      ll_store(&rows[par * G + blockIdx.x].v[lane], S[lane * PPITCH + lr], tag);
-      if (blockIdx.x == 0) ll_store(&rowj[par].v[lane], S[lane * PPITCH + j], tag);  // row j lives in CTA 0
+      if (lane == 0) ll_store_u(&hd[blockIdx.x].key, ml, mh, tag);
+      const int bw = ((int)br - (int)row0) >> 5;  // the CTA's candidate row is always one of its own live rows
+      PanelRow* myrow = &rows[par * G + blockIdx.x];
+      ll_store(&myrow->v[lane], s_cand[bw][lane], tag);
+      if (blockIdx.x == 0) ll_store(&rowj[par].v[lane], s_rowj_out[lane], tag);
       if (lane == 0) {
-        PanelHdr* h = &hdrs[par * G + blockIdx.x];
-        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(&h->absval), "r"(ml), "r"(tag), "r"(mh), "r"(tag) : "memory");
-        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(&h->row), "r"(br), "r"(tag), "r"(0u), "r"(tag) : "memory");
+        ll_store(&myrow->v[PW], s_cand[bw][PW], tag);
+        ll_store_u(&myrow->row, br, 0u, tag);
       }
-      if (dbg) t2 = clock64();
-      // every lane keeps the best of its slots, then the warp reduces
-      unsigned whi = 0, wlo = 0, wrow = 0x7fffffffu, wslot = 0;
-      for (int q = lane; q < G; q += 32) {
-        const PanelHdr* h = &hdrs[par * G + q];
-        unsigned a0, t0, a1, t1, r0, t2, r1 = 0, t3;
-        bool ok;
-        do {
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a0), "=r"(t0), "=r"(a1), "=r"(t1) : "l"(&h->absval) : "memory");
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(t2), "=r"(r1), "=r"(t3) : "l"(&h->row) : "memory");
-          ok = t0 == tag && t1 == tag && t2 == tag && t3 == tag;
-        } while (!ok);
-        bool better = a1 > whi || (a1 == whi && (a0 > wlo || (a0 == wlo && r0 < wrow)));
-        if (better) { whi = a1; wlo = a0; wrow = r0; wslot = (unsigned)q; }
-      }
-      mh = __reduce_max_sync(0xffffffffu, whi);
-      c1 = whi == mh;
-      ml = __reduce_max_sync(0xffffffffu, c1 ? wlo : 0u);
-      c2 = c1 && wlo == ml;
-      const unsigned wr = __reduce_min_sync(0xffffffffu, c2 ? wrow : 0x7fffffffu);
-      const unsigned ws = __reduce_min_sync(0xffffffffu, (c2 && wrow == wr) ? wslot : 0x7fffffffu);
-      if (dbg) t3 = clock64();
-      double pv, rj;
-      bool ok1, ok2;
-      do {  // both rows in flight together
-        ok1 = ll_load(&rows[par * G + ws].v[lane], tag, pv);
-        ok2 = ll_load(&rowj[par].v[lane], tag, rj);
-      } while (!(ok1 && ok2));
-      s_prow[lane] = pv;
-      s_rowj[lane] = rj;
-      if (lane == 0) s_piv = (int)wr;
-      if (dbg) t4 = clock64();
     }
-    __syncthreads();
-    if (dbg) t5 = clock64();
-    const int p = s_piv;
-    const double piv = s_prow[j];
-    if (blockIdx.x == 0 && tid == 0) {
-      ipiv[off + j] = (int)(off + p + 1);
-      if (piv == 0.0 && *info == 0) *info = (int)(off + j + 1);
-    }
-    // ---- 3. swap (only when the pivot is non-zero, as DGETF2 does), scale, rank-1 update
-    __shared__ long long s_dbg[4];
-    if (dbg && tid == PR - 1) s_dbg[0] = clock64();
-    const bool swapped = (piv != 0.0) && (p != j);
-    double rinv = 1.0;
-    if (piv != 0.0 && fabs(piv) >= sfmin) rinv = 1.0 / piv;
-    // The two rows of the interchange are rewritten by whole warps (lane c handles column c): a
-    // single thread walking 32 shared-memory cells would be the critical path of the column.
-    if (swapped && warp == 1 && blockIdx.x == 0) S[lane * PPITCH + j] = s_prow[lane];  // row j <- pivot row
-    if (swapped && warp == 2 && p >= row0 && p < row0 + PR) {                             // row p <- old row j, updated
-      const double ajp = s_rowj[j];
-      const double lp = (fabs(piv) >= sfmin) ? ajp * rinv : ajp / piv;
-      double val = s_rowj[lane];
-      if (lane == j) val = lp;
-      else if (lane > j) val = __dsub_rn(val, __dmul_rn(lp, s_prow[lane]));
-      S[lane * PPITCH + (p - (int)row0)] = val;
-    }
-    if (dbg && tid == PR - 1) s_dbg[1] = clock64();
-    if (live && grow > j && !(swapped && (int)grow == p)) {
-      const double aj = S[j * PPITCH + tid];
-      double l = aj;
-      if (piv != 0.0) l = (fabs(piv) >= sfmin) ? aj * rinv : aj / piv;
-      S[j * PPITCH + tid] = l;
-      // s_prow is row j of the panel after the interchange (a zero pivot implies p == j).
-      // Groups of 8 columns: all loads first, then the FMAs, then the stores (the compiler cannot
-      // prove that S and s_prow do not alias, so a plain loop would serialise on shared-memory latency)
+    if (DBG) tk[2] = clock64();
+    // ---- the rest of the pending rank-1 update (columns j+1 ..), in the shadow of the exchange.
+    // Groups of 8 columns: all loads first, then the arithmetic, then the stores (the compiler cannot
+    // prove that S and s_prow do not alias, so a plain loop would serialise on shared-memory latency)
+    if (upd) {
       for (int c8 = (j + 1) & ~7; c8 < PW; c8 += 8) {
         double av[8], pv[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) { av[q] = S[(c8 + q) * PPITCH + tid]; pv[q] = s_prow[c8 + q]; }
+        for (int t = 0; t < 8; t++) { av[t] = S[(c8 + t) * PPITCH + tid]; pv[t] = prow[c8 + t]; }
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-          if (c8 + q > j) S[(c8 + q) * PPITCH + tid] = __dsub_rn(av[q], __dmul_rn(l, pv[q]));
+        for (int t = 0; t < 8; t++)
+          if (c8 + t > j) S[(c8 + t) * PPITCH + tid] = __dsub_rn(av[t], __dmul_rn(lmul, pv[t]));
       }
     }
-    if (dbg && tid == PR - 1) s_dbg[2] = clock64();
-    __syncthreads();  // s_prow / s_rowj / s_piv / s_val are rewritten in the next column
-    if (dbg && tid == 0 && blockIdx.x == 0) {
-      long long t6 = clock64();
-      atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)(t1 - t0));
-      atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(t2 - t1));
-      atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(t3 - t2));
-      atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)(t4 - t3));
-      atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)(t5 - t4));
-      atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)(t6 - t5));
-      atomicAdd((unsigned long long*)&dbg[6], 1ull);
-      atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)(s_dbg[2] - s_dbg[1]));
-      atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(s_dbg[1] - s_dbg[0]));
-      atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(t6 - s_dbg[2]));
+    if (j == nsteps) break;
+    if (DBG) tk[3] = clock64();
+    if (warp == 0) {
+      // ---- wait for every CTA's key (all of a lane's slots in flight together), pick the winner
+      unsigned whi = 0, wlo = 0, wslot = 0x7fffffffu;
+      for (int base = 0; base < G; base += 128) {
+        unsigned a[4], b[4];
+        bool done[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) done[t] = base + t * 32 + lane >= G;
+        bool all;
+        do {
+          all = true;
+#pragma unroll
+          for (int t = 0; t < 4; t++)
+            if (!done[t]) {
+              done[t] = ll_load_u(&hd[base + t * 32 + lane].key, tag, a[t], b[t]);
+              all = all && done[t];
+            }
+        } while (!all);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int slot = base + t * 32 + lane;
+          if (slot < G && (b[t] > whi || (b[t] == whi && a[t] > wlo) || wslot == 0x7fffffffu)) {
+            whi = b[t]; wlo = a[t]; wslot = (unsigned)slot;   // slots ascend within a lane: strict > keeps the first
+          }
+        }
+      }
+      const unsigned mh = __reduce_max_sync(0xffffffffu, whi);
+      const bool c1 = whi == mh && wslot != 0x7fffffffu;
+      const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? wlo : 0u);
+      const bool c2 = c1 && wlo == ml;
+      const unsigned ws = __reduce_min_sync(0xffffffffu, c2 ? wslot : 0x7fffffffu);
+      if (DBG) tk[4] = clock64();
+      // ---- fetch the winner's row and the old row j, both in flight together
+      const PanelRow* win = &rows[par * G + ws];
+      double pv, rj, ri = 0.0;
+      unsigned wr = 0, dummy;
+      bool ok1, ok2, ok3, ok4;
+      do {  // every lane issues the same four loads (no divergent round trips): 2 x 512 bytes + two broadcast words
+        ok1 = ll_load(&win->v[lane], tag, pv);
+        ok2 = ll_load(&rowj[par].v[lane], tag, rj);
+        ok3 = ll_load_u(&win->row, tag, wr, dummy);
+        ok4 = ll_load(&win->v[PW], tag, ri);
+      } while (!(ok1 && ok2 && ok3 && ok4));
+      s_prow[par][lane] = pv;
+      s_rowq[lane] = rj;
+      if (lane == 0) s_piv = (int)wr;
+      if (lane == 1) s_rinv = ri;
+      if (DBG) tk[5] = clock64();
+    }
+    __syncthreads();
+    if (DBG && tid == 0 && blockIdx.x == gridDim.x / 2) {  // phases of warp 0 of a middle CTA, cycles summed over columns
+      tk[6] = clock64();
+      for (int t = 0; t < 6; t++) atomicAdd(&dbg[t], (unsigned long long)(tk[t + 1] - tk[t]));
+      atomicAdd(&dbg[6], 1ull);
     }
   }
+  __syncthreads();
 
   if (live) {
 #pragma unroll
@@ -362,26 +420,31 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   PanelRow* rj_ = L.rowj;
   unsigned epoch = g_panel_epoch++ & 0x03ffffffu;
   if (epoch == 0) epoch = g_panel_epoch++ & 0x03ffffffu;
-  static long long* dbg = nullptr;
+  // LLACUDA_PANEL_DBG=1: per-column phase breakdown of the exchange (instrumented instantiation of the kernel)
+  static unsigned long long* dbg = nullptr;
   static bool dbg_checked = false;
   if (!dbg_checked) {
     dbg_checked = true;
     if (getenv("LLACUDA_PANEL_DBG")) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
   }
-  if (dbg && getenv("LLACUDA_PANEL_DBG_DUMP") && (g_panel_epoch % 64) == 0) {
-    long long h[16];
+  if (dbg && (g_panel_epoch % 128) == 0) {
+    unsigned long long h[16];
     cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
-    if (h[6]) fprintf(stderr, "  update detail: pre=%lld loop=%lld tail-sync=%lld\n", h[8] / h[6], h[7] / h[6], h[9] / h[6]);
-    if (h[6]) fprintf(stderr, "panel phases (cycles/step over %lld steps): cand=%lld pub=%lld poll=%lld fetch=%lld sync=%lld update=%lld\n",
-                      h[6], h[0] / h[6], h[1] / h[6], h[2] / h[6], h[3] / h[6], h[4] / h[6], h[5] / h[6]);
+    if (h[6]) fprintf(stderr, "panel phases, cycles/column over %llu columns (m=%lld): apply+cand=%llu publish=%llu own-update=%llu poll=%llu fetch=%llu sync=%llu\n",
+                      h[6], (long long)m, h[0] / h[6], h[1] / h[6], h[2] / h[6], h[3] / h[6], h[4] / h[6], h[5] / h[6]);
+    cudaMemset(dbg, 0, 128);
   }
+  static const bool leaf_trace = getenv("LLACUDA_TRACE_LEAF") != nullptr;
+  if (leaf_trace) trace_mark(L.st, "lu.leaf>", j0, m);
   void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &h_, &r_, &rj_, &epoch, &dbg};
-  LLA_CUDA(cudaLaunchCooperativeKernel((void*)lla_dgetf2_panel_kernel, dim3(G), dim3(PR), args, PANEL_SMEM, L.st));
+  LLA_CUDA(cudaLaunchCooperativeKernel(dbg ? (void*)lla_dgetf2_panel_kernel<true> : (void*)lla_dgetf2_panel_kernel<false>, dim3(G), dim3(PR), args, PANEL_SMEM, L.st));
   count_launch();
+  if (leaf_trace) trace_mark(L.st, "lu.leafK<", j0, m);
   // interchange the other columns of the swap window now: [swap_c0, j0) and [j0+w, swap_c1)
   int64_t npiv = m < w ? m : w;
   LLA_TRY(dlaswp_skip_dev(L.swap_c1 - L.swap_c0, j0 - L.swap_c0, j0 + w - L.swap_c0, L.A + L.swap_c0 * L.lda, L.lda,
                           j0, j0 + npiv, L.ipiv, true, L.st, nullptr));
+  if (leaf_trace) trace_mark(L.st, "lu.leaf<", j0, m);
   return 0;
 }
 
@@ -428,8 +491,11 @@ static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int
   const int64_t nc = c1 - c0;
   double* A11 = L.A + k + k * L.lda;
   double* A12 = L.A + k + c0 * L.lda;
+  static const bool upd_trace = getenv("LLACUDA_TRACE_LEAF") != nullptr;
   LLA_TRY(dlaswp_dev(nc, L.A + c0 * L.lda, L.lda, k, k + kb, L.ipiv, true, st));
+  if (upd_trace) trace_mark(st, "lu.upd.swp<", k, nc);
   LLA_TRY(dtrsm_left_inv_dev(false, 0, kb, nc, A11, L.lda, L.linv + (k / IB) * IB * IB, A12, L.lda, st));
+  if (upd_trace) trace_mark(st, "lu.upd.trsm<", k, nc);
   if (L.M > k + kb)
     LLA_TRY(dgemm_dev(0, 0, L.M - k - kb, nc, kb, -1.0, A11 + kb, L.lda, A12, L.lda, 1.0, A12 + kb, L.lda, TRI_FULL, st,
                       nullptr, hint));
@@ -460,7 +526,9 @@ static int lu_blocked(LuCtx L) {
     // ---- panel k on s2
     LuCtx P = L;
     P.st = s2; P.swap_c0 = k; P.swap_c1 = k + kb;
+    trace_mark(s2, "lu.panel>", k, kb);
     LLA_TRY(lu_rec(P, k, L.M - k, kb));
+    trace_mark(s2, "lu.panel<", k, kb);
     LLA_CUDA(cudaEventRecord(ev_panel, s2));
     // ---- interchanges of the finished columns [0, k) on s3 (after the update that still reads them)
     if (k > 0) {
@@ -475,7 +543,9 @@ static int lu_blocked(LuCtx L) {
     LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
     const int64_t next_kb = (k + kb < mn) ? ((mn - c0) < NB ? (mn - c0) : NB) : 0;
     const int64_t c1 = c0 + next_kb;
+    trace_mark(s1, "lu.updA>", k, c1 - c0);
     LLA_TRY(lu_update_cols(L, k, kb, c0, c1, s1));
+    trace_mark(s1, "lu.updA<", k, c1 - c0);
     LLA_CUDA(cudaEventRecord(ev_a, s1));
     LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
     // the rest of the update runs as a persistent GEMM that leaves `reserve` SMs to the panel stream:
@@ -484,6 +554,7 @@ static int lu_blocked(LuCtx L) {
     if (reserve < 0) { const char* e = getenv("LLACUDA_LU_RESERVE"); reserve = e ? atoi(e) : 0; }  // measured: no gain on B200 (profiles/r01_lu_tuning.txt), off by default
     const bool overlap = (c1 < L.N) && (k + kb < mn);
     LLA_TRY(lu_update_cols(L, k, kb, c1, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
+    trace_mark(s1, "lu.updB<", k, L.N - c1);
     LLA_CUDA(cudaEventRecord(ev_b, s1));
     have_b = true;
   }
@@ -501,8 +572,9 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   // co-residency bound of the cooperative panel kernel
   static int per_sm = 0;
   if (per_sm == 0) {
-    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel, PR, PANEL_SMEM));
+    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel<false>, PR, PANEL_SMEM));
   }
   if ((int64_t)per_sm * c->sm_count < maxG) {
     set_error(__FILE__, __LINE__, "dgetrf: panel too tall for one cooperative launch", (int)m);

@@ -16,6 +16,7 @@
 #include "../../include/llacuda.h"
 
 #include <cstdlib>
+#include <cstdio>
 
 namespace llacuda {
 
@@ -24,29 +25,47 @@ namespace llacuda {
 // the GEMM-only triangular solves of the levels above.
 __global__ void __launch_bounds__(T128_THREADS) lla_dpotrf128_kernel(int r, double* __restrict__ A, int64_t lda,
                                                                      double* __restrict__ uinv, int off,
-                                                                     int* __restrict__ info) {
+                                                                     int* __restrict__ info, long long* dbg) {
   if (*info != 0) return;
+  long long tk[6];
+  if (dbg) tk[0] = clock64();
   extern __shared__ __align__(16) double sm128[];
   double* S = sm128;
   double* tmp = sm128 + T128 * T128_SP;
   const int tid = threadIdx.x;
   tri128_load_lower(S, A, lda, r, /*src_upper=*/true, /*unit=*/false, tid);
   __syncthreads();
-  const int fail = potrf128_lower_smem(S, r, tid);
+  if (dbg) tk[1] = clock64();
+  const int fail = potrf128_lower_smem(S, tmp, r, tid);
   if (fail != 0) {  // leading minor off+fail is not positive definite: flag it, later kernels skip
     if (tid == 0) *info = off + fail;
     return;
   }
+  if (dbg) tk[2] = clock64();
   tri128_store(S, A, lda, r, /*dst_upper=*/true, /*zero_other=*/false, tid);
   __syncthreads();
-  trtri128_lower_smem(S, tmp, /*unit=*/false, tid);
+  if (dbg) tk[3] = clock64();
+  trtri128_lower_smem(S, tmp, /*unit=*/false, tid, /*have_rdiag=*/true);
+  if (dbg) tk[4] = clock64();
   tri128_store(S, uinv, IB, IB, /*dst_upper=*/true, /*zero_other=*/true, tid);
+  if (dbg && tid == 0) {
+    tk[5] = clock64();
+    for (int t = 0; t < 5; t++) dbg[t] = tk[t + 1] - tk[t];
+  }
 }
 
 static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, double* uinv, int* info, cudaStream_t st) {
   if (n <= 0) return 0;
   if (n <= IB) {
-    lla_dpotrf128_kernel<<<1, T128_THREADS, T128_SMEM, st>>>((int)n, A, lda, uinv, (int)off, info);
+    static long long* dbg = nullptr;
+    static bool dbg_checked = false;
+    if (!dbg_checked) { dbg_checked = true; if (getenv("LLACUDA_LEAF_DBG")) cudaMalloc(&dbg, 64); }
+    lla_dpotrf128_kernel<<<1, T128_THREADS, T128_SMEM, st>>>((int)n, A, lda, uinv, (int)off, info, dbg);
+    if (dbg) {
+      long long h[5];
+      cudaMemcpy(h, dbg, 40, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "potrf128 phases (cycles): load=%lld factor=%lld store=%lld trtri=%lld store-inv=%lld\n", h[0], h[1], h[2], h[3], h[4]);
+    }
     count_launch();
     LLA_CUDA(cudaGetLastError());
     return 0;
@@ -85,8 +104,11 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     double* Arow = Akk + kb * lda;             // block row right of the diagonal block
     double* uk = uinv + (k / IB) * IB * IB;
     // ---- panel k on s2 (its inputs were produced by part (a) of the previous update)
+    trace_mark(s2, "chol.panel>", k, kb);
     LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, s2));
+    trace_mark(s2, "chol.trsm>", k, n2);
     if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, s2, info));
+    trace_mark(s2, "chol.panel<", k, kb);
     LLA_CUDA(cudaEventRecord(ev_panel, s2));
     if (n2 <= 0) break;
     // ---- trailing update of step k on s1
@@ -94,14 +116,27 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     const int64_t kb_next = n2 < NB ? n2 : NB;
     double* Anext = Arow + kb;                   // A[k+kb, k+kb]
     // (a) block row of the next panel: rows [k+kb, k+kb+kb_next), columns [k+kb, n)
+    trace_mark(s1, "chol.updA>", k, n2);
     LLA_TRY(dgemm_dev(1, 0, kb_next, n2, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, s1, info));
+    trace_mark(s1, "chol.updA<", k, n2);
     LLA_CUDA(cudaEventRecord(ev_row, s1));
     LLA_CUDA(cudaStreamWaitEvent(s2, ev_row, 0));
     // (b) the rest: rows [k+kb+kb_next, n)
     const int64_t n3 = n2 - kb_next;
-    if (n3 > 0)
-      LLA_TRY(dgemm_dev(1, 0, n3, n3, kb, -1.0, Arow + kb_next * lda, lda, Arow + kb_next * lda, lda, 1.0,
-                        Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info, getenv("LLACUDA_CHOL_RESERVE") ? GEMM_RESERVE_SMS : GEMM_AUTO));
+    if (n3 > 0) {
+      // k-split of the big update: shorter-lived CTAs, so that the kernels of the panel chain (high-priority
+      // stream) find a free SM sooner (a 128x128 tile with k = 1024 occupies its SM for ~150 us)
+      static int64_t ks_env = -1;
+      if (ks_env < 0) { const char* e = getenv("LLACUDA_CHOL_KSPLIT"); ks_env = e ? atoi(e) : 0; }
+      const int64_t ks = ks_env > 0 ? ks_env : kb;
+      for (int64_t kk = 0; kk < kb; kk += ks) {
+        const int64_t kw = (kb - kk) < ks ? (kb - kk) : ks;
+        const double* P = Arow + kk + kb_next * lda;
+        LLA_TRY(dgemm_dev(1, 0, n3, n3, kw, -1.0, P, lda, P, lda, 1.0, Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info,
+                          getenv("LLACUDA_CHOL_RESERVE") ? GEMM_RESERVE_SMS : GEMM_AUTO));
+      }
+    }
+    trace_mark(s1, "chol.updB<", k, n3);
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   return 0;

@@ -48,17 +48,24 @@ __device__ __forceinline__ void smem_mm(double* C, int ldc, const double* A, int
 // On return S holds inv(S).  inv([L11 0; L21 L22]) = [X11 0; -X22 L21 X11, X22], applied at the
 // 32 -> 64 -> 128 levels; the 32 x 32 diagonal blocks are inverted by forward substitution on the
 // identity, one thread per column with the column in registers.
-__device__ __forceinline__ void trtri128_lower_smem(double* S, double* tmp, bool unit, int tid) {
+// `have_rdiag`: tmp[0..127] already holds the reciprocals of the diagonal (the Cholesky leaf leaves them
+// there); otherwise they are computed first, so that the substitution chain multiplies instead of dividing.
+__device__ __forceinline__ void trtri128_lower_smem(double* S, double* tmp, bool unit, int tid, bool have_rdiag = false) {
+  if (!have_rdiag) {
+    if (tid < 128) tmp[tid] = unit ? 1.0 : 1.0 / S[tid + tid * T128_SP];
+    __syncthreads();
+  }
   // ---- 32 x 32 diagonal blocks
   double x[32];
   const int b = tid >> 5, c = tid & 31;
   if (tid < 128) {
     const double* D = S + (32 * b) + (32 * b) * T128_SP;
+    const double* rd = tmp + 32 * b;
 #pragma unroll
     for (int i = 0; i < 32; i++) x[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 0; k < 32; k++) {
-      if (!unit) x[k] = x[k] / D[k + k * T128_SP];
+      x[k] = x[k] * rd[k];
 #pragma unroll
       for (int i = k + 1; i < 32; i++) x[i] = fma(-D[i + k * T128_SP], x[k], x[i]);
     }
@@ -120,72 +127,99 @@ __device__ __forceinline__ void tri128_store(const double* S, double* __restrict
   }
 }
 
-// In-place lower Cholesky S = L L^T of the leading r x r block, left-looking in 32-column panels.
-// A panel first receives the updates of all earlier columns (4 x 4 register tiles), then is
-// factored column by column straight in shared memory: thread (i, h) owns row i and every 4th
-// column of the panel.  One barrier per column: column g is scaled on the fly (x * rsqrt(d)) and its
-// scaled values are written back one step later, when nobody reads the unscaled ones any more.
-// These loops are latency bound (a few warps on one SM), hence the low instruction count per step.
-// Returns 0, or k+1 for the first non-positive / NaN pivot (uniform across the CTA).
-__device__ __forceinline__ int potrf128_lower_smem(double* S, int r, int tid) {
-  const int i = tid & 127, h = tid >> 7;  // T128_THREADS = 512: h in 0..3
+// In-place lower Cholesky S = L L^T of the leading r x r block (S is identity-padded to 128 x 128),
+// right-looking over 32-column block steps:
+//   (1) warp 0 factors the 32 x 32 diagonal block in registers (lane = row; the pivot column travels by
+//       shuffles, the reciprocal square root of the next pivot is in flight while the current column's
+//       updates issue) and leaves 1 / l_kk in rdiag;
+//   (2) one thread per row below solves its row against L11^T by substitution (L11 read as broadcasts);
+//   (3) the whole CTA applies the rank-32 update to the lower triangle of the trailing block, 4 x 4
+//       register tiles enumerated over the triangle only.
+// Returns 0, or k+1 for the first non-positive / NaN pivot (uniform across the CTA).  rdiag: 128 doubles.
+__device__ __forceinline__ int potrf128_lower_smem(double* S, double* rdiag, int r, int tid) {
+  __shared__ int s_fail;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid < 128) rdiag[tid] = 1.0;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
   for (int c0 = 0; c0 < r; c0 += 32) {
-    if (c0 > 0) {
-      // S[c0.., c0..c0+31] -= L[c0.., 0..c0) * L[c0..c0+31, 0..c0)^T
-      const int tiles_m = (T128 - c0) / 4;
-      for (int t = tid; t < tiles_m * 8; t += T128_THREADS) {
-        const int i0 = c0 + (t % tiles_m) * 4, j0 = c0 + (t / tiles_m) * 4;
-        double acc[4][4];
+    if (warp == 0) {
+      double a[32];
+      double* D = S + (c0 + lane) + c0 * T128_SP;  // row c0 + lane
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+      for (int c = 0; c < 32; c++) a[c] = D[c * T128_SP];
+      int fail = 0;
 #pragma unroll
-          for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < c0; k++) {
-          double av[4], bv[4];
+      for (int k = 0; k < 32; k++) {
+        const double d = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(d > 0.0)) { fail = c0 + k + 1; break; }
+        const double rs = rsqrt(d);
+        double l = a[k] * rs;
+        if (lane == k) l = sqrt(d);
+        a[k] = l;
+        if (lane == 0) rdiag[c0 + k] = rs;
 #pragma unroll
-          for (int a = 0; a < 4; a++) av[a] = S[i0 + a + k * T128_SP];
+        for (int c = k + 1; c < 32; c++) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);  // meaningful for rows >= c only
+      }
+      if (fail) {
+        if (lane == 0) s_fail = fail;
+      } else {
 #pragma unroll
-          for (int b = 0; b < 4; b++) bv[b] = S[j0 + b + k * T128_SP];
-#pragma unroll
-          for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b = 0; b < 4; b++)
-            if (i0 + a >= j0 + b) S[i0 + a + (j0 + b) * T128_SP] -= acc[a][b];
+        for (int c = 0; c < 32; c++)
+          if (c <= lane) D[c * T128_SP] = a[c];
       }
     }
     __syncthreads();
-    double lprev = 0.0, dprev = 0.0;  // deferred write-back of the previous column
-    const int kend = (r - c0) < 32 ? (r - c0) : 32;
-#pragma unroll 1
-    for (int k = 0; k < kend; k++) {
-      const int g = c0 + k;
-      if (k > 0 && h == 0) {
-        if (i == g - 1) S[i + (g - 1) * T128_SP] = dprev;
-        else if (i > g - 1) S[i + (g - 1) * T128_SP] = lprev;
+    if (s_fail) return s_fail;
+    const int t0 = c0 + 32;          // first row / column of the trailing block
+    const int nbelow = T128 - t0;
+    if (nbelow <= 0) break;
+    if (tid >= 32 && tid < 32 + nbelow) {
+      double x[32];
+      double* R = S + (t0 + tid - 32) + c0 * T128_SP;
+      const double* L11 = S + c0 + c0 * T128_SP;
+#pragma unroll
+      for (int c = 0; c < 32; c++) x[c] = R[c * T128_SP];
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        x[k] *= rdiag[c0 + k];
+#pragma unroll
+        for (int c = k + 1; c < 32; c++) x[c] = fma(-x[k], L11[c + k * T128_SP], x[c]);
       }
-      const double d = S[g + g * T128_SP];
-      if (!(d > 0.0)) return g + 1;
-      const double rs = rsqrt(d);
-      const double li = S[i + g * T128_SP] * rs;
-      lprev = li;
-      dprev = sqrt(d);
-      if (i > g) {
-        const int cend = (i < c0 + 31) ? i : (c0 + 31);
-        for (int c = g + 1 + h; c <= cend; c += 4)
-          S[i + c * T128_SP] = fma(-li, S[c + g * T128_SP] * rs, S[i + c * T128_SP]);
-      }
-      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 32; c++) R[c * T128_SP] = x[c];
     }
-    if (h == 0) {
-      const int g = c0 + kend - 1;
-      if (i == g) S[i + g * T128_SP] = dprev;
-      else if (i > g) S[i + g * T128_SP] = lprev;
+    __syncthreads();
+    // trailing block: tiles (ti >= tj) of the T x T tile triangle, folded into a (T/2) x (T+1) rectangle
+    const int T = nbelow / 4;
+    for (int t = tid; t < (T / 2) * (T + 1); t += T128_THREADS) {
+      const int pp = t / (T + 1), qq = t % (T + 1);
+      int ti, tj;
+      if (qq <= T / 2 + pp) { ti = T / 2 + pp; tj = qq; }
+      else { ti = T / 2 - 1 - pp; tj = qq - (T / 2 + pp + 1); }
+      const int i0 = t0 + 4 * ti, j0 = t0 + 4 * tj;
+      double acc[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < 32; k++) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) av[u] = S[i0 + u + (c0 + k) * T128_SP];
+#pragma unroll
+        for (int v = 0; v < 4; v++) bv[v] = S[j0 + v + (c0 + k) * T128_SP];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int v = 0; v < 4; v++) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+          if (i0 + u >= j0 + v) S[i0 + u + (j0 + v) * T128_SP] -= acc[u][v];
     }
     __syncthreads();
   }

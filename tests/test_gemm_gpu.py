@@ -211,7 +211,8 @@ def test_gemm_degenerate_shapes():
     rng = np.random.default_rng(3)
     c = rng.uniform(-1, 1, (4, 5))
     # k = 0: C = beta * C, A and B are never read
-    got = L.gemm(1.0, np.zeros((4, 0)), np.zeros((0, 5)), 0.5, c.copy(), k=0, lda=1, ldb=5)
+    # (padded operands with k = 0 logical columns: gemm!'s own asserts, src/blas.lisp:40-53, need lda >= 1 rows to exist)
+    got = L.gemm(1.0, np.zeros((4, 1)), np.zeros((1, 5)), 0.5, c.copy(), k=0, lda=1, ldb=5)
     assert np.allclose(got, 0.5 * c, rtol=0, atol=1e-16)
     # m = 0 / n = 0: nothing happens
     e = np.zeros((0, 5))
