@@ -20,7 +20,7 @@ namespace llacuda {
 constexpr int BN32 = 32;
 
 template <int NR>
-__global__ void __launch_bounds__(256) lla_dgesv_batched_kernel(int n, int nrhs, int64_t batch, double* __restrict__ A,
+__global__ void __launch_bounds__(128, 5) lla_dgesv_batched_kernel(int n, int nrhs, int64_t batch, double* __restrict__ A,
                                                                 int64_t strideA, int* __restrict__ ipiv,
                                                                 double* __restrict__ B, int64_t strideB,
                                                                 int* __restrict__ info, int keep_lu) {
@@ -133,7 +133,7 @@ int dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t strideA
     set_error(__FILE__, __LINE__, "dgesv_batched: supported sizes are n <= 32, nrhs <= 8", n);
     return LLACUDA_ERR_BAD_ARG;
   }
-  const int warps = 8;
+  const int warps = 4;  // 128-thread CTAs: 5 fit the register file at 100 registers per thread (20 warps per SM; 256-thread CTAs stop at 16)
   unsigned grid = (unsigned)((batch + warps - 1) / warps);
 #define LLA_BATCHED(NR) lla_dgesv_batched_kernel<NR><<<grid, warps * 32, 0, st>>>(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu)
   if (nrhs <= 1) LLA_BATCHED(1);

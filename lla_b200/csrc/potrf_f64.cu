@@ -59,7 +59,7 @@ static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, double* uin
   if (n <= IB) {
     static long long* dbg = nullptr;
     static bool dbg_checked = false;
-    if (!dbg_checked) { dbg_checked = true; if (getenv("LLACUDA_LEAF_DBG")) cudaMalloc(&dbg, 64); }
+    if (!dbg_checked) { dbg_checked = true; if (getenv("LLACUDA_LEAF_DBG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); } }
     lla_dpotrf128_kernel<<<1, T128_THREADS, T128_SMEM, st>>>((int)n, A, lda, uinv, (int)off, info, dbg);
     if (dbg) {
       long long h[5];

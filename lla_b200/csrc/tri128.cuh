@@ -17,9 +17,11 @@ constexpr size_t T128_SMEM = (size_t)(T128 * T128_SP + 64 * 64) * sizeof(double)
 template <int M, int N, int K>
 __device__ __forceinline__ void smem_mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb,
                                         double alpha, int tid, int nth) {
+  // tile t owns rows {ti, ti + TM, ti + 2 TM, ti + 3 TM} and columns 4 tj .. 4 tj + 3: consecutive lanes read
+  // consecutive rows of A (conflict-free 64-bit shared loads) and broadcast-read B
   constexpr int TM = M / 4, TN = N / 4;
   for (int t = tid; t < TM * TN; t += nth) {
-    const int i0 = (t % TM) * 4, j0 = (t / TM) * 4;
+    const int ti = t % TM, j0 = (t / TM) * 4;
     double acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -29,7 +31,7 @@ __device__ __forceinline__ void smem_mm(double* C, int ldc, const double* A, int
     for (int k = 0; k < K; k++) {
       double av[4], bv[4];
 #pragma unroll
-      for (int a = 0; a < 4; a++) av[a] = A[i0 + a + k * lda];
+      for (int a = 0; a < 4; a++) av[a] = A[ti + a * TM + k * lda];
 #pragma unroll
       for (int b = 0; b < 4; b++) bv[b] = B[k + (j0 + b) * ldb];
 #pragma unroll
@@ -40,7 +42,7 @@ __device__ __forceinline__ void smem_mm(double* C, int ldc, const double* A, int
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int b = 0; b < 4; b++) C[i0 + a + (j0 + b) * ldc] = alpha * acc[a][b];
+      for (int b = 0; b < 4; b++) C[ti + a * TM + (j0 + b) * ldc] = alpha * acc[a][b];
   }
 }
 
@@ -103,14 +105,26 @@ __device__ __forceinline__ void trtri128_lower_smem(double* S, double* tmp, bool
 // with the identity to 128 x 128; the strict upper part of S is zeroed.
 __device__ __forceinline__ void tri128_load_lower(double* S, const double* __restrict__ T, int64_t ldt, int r,
                                                   bool src_upper, bool unit, int tid) {
-  for (int idx = tid; idx < T128 * T128; idx += T128_THREADS) {
-    const int i = idx & 127, j = idx >> 7;  // consecutive threads run down a column of T
-    double v = 0.0;
-    const bool in_tri = src_upper ? (i <= j) : (i >= j);
-    if (i < r && j < r && in_tri && !(unit && i == j)) v = T[i + (int64_t)j * ldt];
-    if (i == j && (unit || i >= r)) v = 1.0;
-    if (src_upper) S[j + i * T128_SP] = v;   // S = T^T
-    else S[i + j * T128_SP] = v;
+  constexpr int PER = T128 * T128 / T128_THREADS;  // 32 elements per thread, 8 loads in flight at a time
+#pragma unroll 1
+  for (int q0 = 0; q0 < PER; q0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int idx = tid + (q0 + q) * T128_THREADS;
+      const int i = idx & 127, j = idx >> 7;  // consecutive threads run down a column of T
+      const bool in_tri = src_upper ? (i <= j) : (i >= j);
+      v[q] = 0.0;
+      if (i < r && j < r && in_tri && !(unit && i == j)) v[q] = T[i + (int64_t)j * ldt];
+      if (i == j && (unit || i >= r)) v[q] = 1.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int idx = tid + (q0 + q) * T128_THREADS;
+      const int i = idx & 127, j = idx >> 7;
+      if (src_upper) S[j + i * T128_SP] = v[q];   // S = T^T
+      else S[i + j * T128_SP] = v[q];
+    }
   }
 }
 
@@ -149,24 +163,33 @@ __device__ __forceinline__ int potrf128_lower_smem(double* S, double* rdiag, int
 #pragma unroll
       for (int c = 0; c < 32; c++) a[c] = D[c * T128_SP];
       int fail = 0;
+      double dmine = 1.0;  // lane k keeps d_k; its square root is taken once, after the loop
+      double d = __shfl_sync(0xffffffffu, a[0], 0);
+      double rs = rsqrt(d);
 #pragma unroll
       for (int k = 0; k < 32; k++) {
-        const double d = __shfl_sync(0xffffffffu, a[k], k);
         if (!(d > 0.0)) { fail = c0 + k + 1; break; }
-        const double rs = rsqrt(d);
-        double l = a[k] * rs;
-        if (lane == k) l = sqrt(d);
-        a[k] = l;
+        if (lane == k) dmine = d;
         if (lane == 0) rdiag[c0 + k] = rs;
+        const double l = a[k] * rs;
+        a[k] = l;
+        double dn = 1.0, rsn = 1.0;
+        if (k + 1 < 32) {  // next pivot first: its reciprocal square root is in flight under the remaining updates
+          a[k + 1] = fma(-l, __shfl_sync(0xffffffffu, l, k + 1), a[k + 1]);
+          dn = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
+          rsn = rsqrt(dn);
+        }
 #pragma unroll
-        for (int c = k + 1; c < 32; c++) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);  // meaningful for rows >= c only
+        for (int c = k + 2; c < 32; c++) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);  // meaningful for rows >= c only
+        d = dn; rs = rsn;
       }
+      const double diag = sqrt(dmine);  // the diagonal itself (lane k's a[k] holds d_k * rs, a rounding away from it)
       if (fail) {
         if (lane == 0) s_fail = fail;
       } else {
 #pragma unroll
         for (int c = 0; c < 32; c++)
-          if (c <= lane) D[c * T128_SP] = a[c];
+          if (c <= lane) D[c * T128_SP] = (c == lane) ? diag : a[c];
       }
     }
     __syncthreads();
@@ -197,7 +220,7 @@ __device__ __forceinline__ int potrf128_lower_smem(double* S, double* rdiag, int
       int ti, tj;
       if (qq <= T / 2 + pp) { ti = T / 2 + pp; tj = qq; }
       else { ti = T / 2 - 1 - pp; tj = qq - (T / 2 + pp + 1); }
-      const int i0 = t0 + 4 * ti, j0 = t0 + 4 * tj;
+      const int i0 = t0 + 4 * ti, j0 = t0 + 4 * tj;  // 16-byte aligned: rows are loaded as two double2 each
       double acc[4][4];
 #pragma unroll
       for (int u = 0; u < 4; u++)
@@ -205,11 +228,10 @@ __device__ __forceinline__ int potrf128_lower_smem(double* S, double* rdiag, int
         for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
 #pragma unroll 8
       for (int k = 0; k < 32; k++) {
-        double av[4], bv[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) av[u] = S[i0 + u + (c0 + k) * T128_SP];
-#pragma unroll
-        for (int v = 0; v < 4; v++) bv[v] = S[j0 + v + (c0 + k) * T128_SP];
+        const double2* ap = reinterpret_cast<const double2*>(S + i0 + (c0 + k) * T128_SP);
+        const double2* bp = reinterpret_cast<const double2*>(S + j0 + (c0 + k) * T128_SP);
+        const double2 a01 = ap[0], a23 = ap[1], b01 = bp[0], b23 = bp[1];
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
