@@ -190,3 +190,27 @@ int dtrsm_left_inv_dev(bool upper, int op, int64_t m, int64_t n, const double* T
 }
 
 }  // namespace llacuda
+
+using namespace llacuda;
+
+// Left-sided triangular solve op(T) X = B in place on device pointers (the DTRSM LLA's trsm% issues,
+// reference src/linear-algebra.lisp:333-347, restricted to side = 'L', alpha = 1): the building block the
+// block-cyclic Cholesky / LU of lla_b200/dist.py runs on the block row that the diagonal owner broadcast.
+extern "C" int llacuda_dtrsm_dev(char uplo, char trans, char diag, int64_t m, int64_t n, const double* T, int64_t ldt,
+                                 double* B, int64_t ldb) {
+  const bool upper = (uplo == 'U' || uplo == 'u'), lower = (uplo == 'L' || uplo == 'l');
+  const bool unit = (diag == 'U' || diag == 'u'), nonunit = (diag == 'N' || diag == 'n');
+  int op = -1;
+  if (trans == 'N' || trans == 'n') op = 0;
+  if (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c') op = 1;
+  if (!(upper || lower) || !(unit || nonunit) || op < 0 || m < 0 || n < 0 || ldt < (m > 1 ? m : 1) || ldb < (m > 1 ? m : 1))
+    return LLACUDA_ERR_BAD_ARG;
+  Context* c = ctx();
+  if (!c) return LLACUDA_ERR_NO_DEVICE;
+  if (m == 0 || n == 0) return 0;
+  Arena ar;
+  LLA_TRY(ar.reserve(tinv_bytes(m) + 1024));
+  double* tinv = (double*)ar.take(tinv_bytes(m));
+  LLA_TRY(dtrtri_blocks_dev(upper, unit, m, T, ldt, tinv, c->stream));
+  return dtrsm_left_inv_dev(upper, op, m, n, T, ldt, tinv, B, ldb, c->stream);
+}

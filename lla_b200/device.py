@@ -72,6 +72,11 @@ def dpotrs(uplo, n, nrhs, A, lda, B, ldb):
     _lib.check(f(uplo.encode(), n, nrhs, A, lda, B, ldb), "dpotrs_dev")
 
 
+def dtrsm(uplo, trans, diag, m, n, T, ldt, B, ldb):
+    f = _sig("llacuda_dtrsm_dev", [_chr, _chr, _chr, _i64, _i64, _vp, _i64, _vp, _i64])
+    _lib.check(f(uplo.encode(), trans.encode(), diag.encode(), m, n, T, ldt, B, ldb), "dtrsm_dev")
+
+
 def dtranspose(rows, cols, src, ldin, dst, ldout):
     f = _sig("llacuda_dtranspose_dev", [_i64, _i64, _vp, _i64, _vp, _i64])
     _lib.check(f(rows, cols, src, ldin, dst, ldout), "dtranspose_dev")

@@ -153,3 +153,269 @@ def summa(grid: Grid, m, n, k, nb, A_loc, B_loc, C_loc, local_gemm=device_gemm, 
             nxt = post(s + 1)
         pending = nxt
     return C_loc
+
+
+# --------------------------------------------------------------------------------------------------
+# Block-cyclic Cholesky (BASELINE.json configs[2]).  The reference has one call
+# site, POTRF('U') on the untransposed row-major buffer (src/linear-algebra.lisp:670-674) followed by
+# POTRS('U') (:296-301); the distributed form keeps that convention: A = U^T U, only the upper
+# triangle of the column-major view is read or written.
+#
+# Local work goes through an `ops` object so that the index / communication logic runs on CPU (gloo)
+# with `TorchOps`; the product path is `DeviceOps` (llacuda kernels on device pointers, no fallback).
+# Every operand is an *image view*: a torch view of shape (cols, rows) whose element [c, r] is the
+# matrix element (r, c) and whose stride(0) is the leading dimension (column-major storage).
+
+class DeviceOps:
+    """llacuda kernels on device pointers: DPOTRF leaf/blocked driver, inverse-based DTRSM, DMMA GEMM."""
+
+    def __init__(self):
+        from . import device as D
+        self.D = D
+        self._info = None
+
+    def _ld(self, img):
+        assert img.stride(1) == 1
+        return img.stride(0) if img.shape[0] > 1 else max(img.shape[1], 1)
+
+    def potrf_upper(self, img):
+        n = img.shape[0]
+        if self._info is None:
+            self._info = torch.zeros(1, dtype=torch.int32, device=img.device)
+        self.D.dpotrf("U", n, img.data_ptr(), self._ld(img), self._info.data_ptr())
+        return self._info   # device scalar; the caller decides when to read it
+
+    def trsm(self, uplo, trans, timg, bimg):
+        m, n = bimg.shape[1], bimg.shape[0]
+        self.D.dtrsm(uplo, trans, "N", m, n, timg.data_ptr(), self._ld(timg), bimg.data_ptr(), self._ld(bimg))
+
+    def gemm(self, opa, m, n, k, alpha, aimg, bimg, beta, cimg, tri=0):
+        """C (m x n) = alpha op(A) B + beta C, op = 'T' or 'N'; tri: 0 full, 1 upper, 2 lower."""
+        self.D.dgemm(opa, "N", m, n, k, alpha, aimg.data_ptr(), self._ld(aimg), bimg.data_ptr(), self._ld(bimg),
+                     beta, cimg.data_ptr(), self._ld(cimg), tri)
+
+
+class TorchOps:
+    """CPU stand-in with the same interface (tests of the distribution logic only)."""
+
+    def potrf_upper(self, img):
+        a = img.t()                                    # matrix view
+        full = torch.triu(a) + torch.triu(a, 1).t()
+        l, info = torch.linalg.cholesky_ex(full)
+        a.copy_(torch.triu(l.t()) + torch.tril(a, -1))  # only the upper triangle is written
+        return info.to(torch.int32).reshape(1)
+
+    def trsm(self, uplo, trans, timg, bimg):
+        t = timg.t()
+        t = torch.triu(t) if uplo == "U" else torch.tril(t)
+        if trans == "T":
+            x = torch.linalg.solve_triangular(t.t(), bimg.t(), upper=(uplo != "U"))
+        else:
+            x = torch.linalg.solve_triangular(t, bimg.t(), upper=(uplo == "U"))
+        bimg.copy_(x.t())
+
+    def gemm(self, opa, m, n, k, alpha, aimg, bimg, beta, cimg, tri=0):
+        a = aimg.t() if opa == "N" else aimg          # op(A): m x k
+        a = a[:m, :k]
+        b = bimg.t()[:k, :n]
+        c = cimg.t()
+        upd = alpha * (a @ b) + beta * c[:m, :n]
+        if tri == 1:
+            upd = torch.triu(upd) + torch.tril(c[:m, :n], -1)
+        elif tri == 2:
+            upd = torch.tril(upd) + torch.triu(c[:m, :n], 1)
+        c[:m, :n] = upd
+
+
+def _count_le(k, r, R):
+    """Number of block indices I <= k with I mod R == r."""
+    return (k - r) // R + 1 if k >= r else 0
+
+
+def pdpotrf(grid: Grid, n, nb, A_loc, ops=None, lookahead=True):
+    """In-place block-cyclic Cholesky A = U^T U of the SPD matrix whose upper triangle is stored in
+    A_loc ((n/Q, n/P) local column-major image, block (I, J) on process (I mod P, J mod Q)).
+    Right-looking; the panel of block step k is
+      1. the owner of the diagonal block factors it (DPOTRF 'U') and broadcasts U_kk along its grid row;
+      2. the processes of that grid row solve U_kk^T X = A(k, J > k) on their blocks of block row k;
+      3. every owner broadcasts its slice of the finished block row to all processes (NCCL over NVLink:
+         nb x (n - k nb) doubles per step, far below the update's work);
+    and the update of step k is one DMMA GEMM per local block column over the blocks (I, J), k < I <= J
+    (the triangular staircase of the block-cyclic layout; diagonal blocks through the masked GEMM).
+    With `lookahead` the update is split: block row k+1 first, then panel k+1 runs on a second stream (its
+    kernels and its broadcasts) while the rest of update k keeps the GPU busy.
+    Returns LAPACK's INFO (0, or the index of the first leading minor that is not positive definite),
+    identical on every rank."""
+    ops = ops or DeviceOps()
+    P, Q, p, q = grid.P, grid.Q, grid.p, grid.q
+    mloc, nloc = n // P, n // Q
+    assert A_loc.shape == (nloc, mloc) and n % (nb * P) == 0 and n % (nb * Q) == 0
+    nblk = n // nb
+    dev, dt = A_loc.device, A_loc.dtype
+    info_acc = torch.zeros(1, dtype=torch.int32, device=dev)
+    multi = P * Q > 1
+    cuda = dev.type == "cuda"
+    # persistent double buffers: the two streams hand them over through events, nothing is freed in the loop
+    pbuf = [[torch.empty((nloc, nb), dtype=dt, device=dev) for _ in range(Q)] for _ in range(2)]
+    wrbuf = [torch.empty((mloc, nb), dtype=dt, device=dev) for _ in range(2)]
+    dblk = torch.empty((nb, nb), dtype=dt, device=dev)
+    main = torch.cuda.current_stream() if cuda else None
+    side = torch.cuda.Stream(priority=-1) if (cuda and lookahead) else main
+    ev_panel = [torch.cuda.Event() for _ in range(2)] if cuda else None
+    ev_rowdone = torch.cuda.Event() if cuda else None
+
+    class _on:  # run a section on `stream`: torch's current stream and llacuda's stream move together
+        def __init__(self, stream): self.stream = stream
+        def __enter__(self):
+            if cuda:
+                self.ctx = torch.cuda.stream(self.stream); self.ctx.__enter__()
+                if hasattr(ops, "D"): ops.D.use_torch_stream()
+        def __exit__(self, *a):
+            if cuda:
+                self.ctx.__exit__(*a)
+                if hasattr(ops, "D"): ops.D.use_torch_stream()
+
+    def panel(k):
+        """Steps 1-3 for block step k; fills pbuf[k % 2] and returns (pieces, first)."""
+        nonlocal info_acc
+        pk, qk = k % P, k % Q
+        lkr = k // P
+        if p == pk:
+            if q == qk:
+                lkc = k // Q
+                diag = A_loc[lkc * nb:(lkc + 1) * nb, lkr * nb:(lkr + 1) * nb]
+                inf = ops.potrf_upper(diag)
+                info_acc += torch.where((info_acc == 0) & (inf != 0), inf + k * nb, torch.zeros_like(inf))
+                dblk.copy_(diag)
+            if Q > 1:
+                dist.broadcast(dblk, src=grid.rank_of(pk, qk), group=grid.row_group)
+            lj0 = _count_le(k, q, Q)
+            if lj0 * nb < nloc:
+                ops.trsm("U", "T", dblk, A_loc[lj0 * nb:, lkr * nb:(lkr + 1) * nb])
+        pieces, first = [], []
+        for qq in range(Q):
+            lj0q = _count_le(k, qq, Q)
+            ncq = nloc - lj0q * nb
+            first.append(lj0q)
+            if ncq <= 0:
+                pieces.append(None)
+                continue
+            buf = pbuf[k % 2][qq][:ncq]
+            if p == pk and q == qq:
+                buf.copy_(A_loc[lj0q * nb:, lkr * nb:(lkr + 1) * nb])
+            if multi:
+                dist.broadcast(buf, src=grid.rank_of(pk, qq))
+            pieces.append(buf)
+        return pieces, first
+
+    def gather_rows(k, pieces, first):
+        """U(k, I) for my block rows I = li P + p > k, stacked in local row order."""
+        li0 = _count_le(k, p, P)
+        nrows = mloc - li0 * nb
+        if nrows <= 0:
+            return None, li0
+        wr = wrbuf[k % 2][:nrows]
+        for li in range(li0, mloc // nb):
+            I = li * P + p
+            idx = I // Q - first[I % Q]
+            wr[(li - li0) * nb:(li - li0 + 1) * nb].copy_(pieces[I % Q][idx * nb:(idx + 1) * nb])
+        return wr, li0
+
+    def update(k, wr, li0, wc, lj0, lo, hi):
+        """A(I, J) -= U(k, I)^T U(k, J) for my blocks with local block row in [lo, hi), k < I <= J."""
+        for lj in range(lj0, nloc // nb):
+            J = lj * Q + q
+            nfull = _count_le(J - 1, p, P)                  # local block rows with I < J are [0, nfull)
+            r0, r1 = max(lo, li0), min(hi, nfull)
+            bj = wc[(lj - lj0) * nb:(lj - lj0 + 1) * nb]
+            if r1 > r0:
+                ops.gemm("T", (r1 - r0) * nb, nb, nb, -1.0, wr[(r0 - li0) * nb:(r1 - li0) * nb], bj, 1.0,
+                         A_loc[lj * nb:(lj + 1) * nb, r0 * nb:r1 * nb])
+            if J % P == p and lo <= J // P < hi:            # the diagonal block (J, J) is mine
+                li = J // P
+                ops.gemm("T", nb, nb, nb, -1.0, wr[(li - li0) * nb:(li - li0 + 1) * nb], bj, 1.0,
+                         A_loc[lj * nb:(lj + 1) * nb, li * nb:(li + 1) * nb], tri=1)
+
+    with _on(side):
+        nxt = panel(0)
+        if cuda: ev_panel[0].record(side)
+    for k in range(nblk):
+        pieces, first = nxt
+        if cuda and side is not main: main.wait_event(ev_panel[k % 2])
+        wc = pieces[q]
+        wr, li0 = gather_rows(k, pieces, first)
+        lj0 = first[q]
+        have = wc is not None and wr is not None
+        # block row k+1 first: it is all that panel k+1 needs
+        own_next = (k + 1 < nblk) and ((k + 1) % P == p)
+        split = li0 + 1 if own_next else li0
+        if have and own_next:
+            update(k, wr, li0, wc, lj0, li0, split)
+        if k + 1 < nblk:
+            if cuda and side is not main:
+                ev_rowdone.record(main); side.wait_event(ev_rowdone)
+            with _on(side):
+                nxt = panel(k + 1)
+                if cuda: ev_panel[(k + 1) % 2].record(side)
+        if have:
+            update(k, wr, li0, wc, lj0, split, mloc // nb)
+    if cuda and side is not main: main.wait_stream(side)
+    if multi:
+        # INFO of the first failing diagonal block wins (smallest positive)
+        big = torch.where(info_acc > 0, info_acc, torch.full_like(info_acc, 2 ** 31 - 1))
+        dist.all_reduce(big, op=dist.ReduceOp.MIN)
+        info_acc = torch.where(big == 2 ** 31 - 1, torch.zeros_like(big), big)
+    return int(info_acc.item())
+
+
+def pdpotrs(grid: Grid, n, nb, U_loc, B, ops=None):
+    """Solves A X = B in place with the block-cyclic factor of pdpotrf (A = U^T U); B is replicated on
+    every rank as the (nrhs, n) column-major image of the n x nrhs right-hand sides (SURVEY.md section 8e:
+    few right-hand sides do not shard; the chain is one small reduction + one broadcast per block)."""
+    ops = ops or DeviceOps()
+    P, Q, p, q = grid.P, grid.Q, grid.p, grid.q
+    mloc, nloc = n // P, n // Q
+    nblk = n // nb
+    nrhs = B.shape[0]
+    dev, dt = B.device, B.dtype
+    multi = P * Q > 1
+    rows_of = lambda cnt: torch.cat([torch.arange((li * P + p) * nb, (li * P + p + 1) * nb) for li in range(cnt)]).to(dev) \
+        if cnt > 0 else None
+    # ---- U^T y = b, block forward substitution down the block columns
+    for k in range(nblk):
+        pk, qk = k % P, k % Q
+        s = torch.zeros((nrhs, nb), dtype=dt, device=dev)
+        if q == qk:
+            cnt = _count_le(k - 1, p, P)                   # my block rows I < k of block column k
+            if cnt > 0:
+                lkc = k // Q
+                yr = B[:, rows_of(cnt)].contiguous()       # (nrhs, cnt nb) image of the known part of y
+                ops.gemm("T", nb, nrhs, cnt * nb, 1.0, U_loc[lkc * nb:(lkc + 1) * nb, :cnt * nb], yr, 0.0, s)
+        if multi:
+            dist.all_reduce(s)
+        yk = (B[:, k * nb:(k + 1) * nb] - s).contiguous()
+        if p == pk and q == qk:
+            ops.trsm("U", "T", U_loc[(k // Q) * nb:(k // Q + 1) * nb, (k // P) * nb:(k // P + 1) * nb], yk)
+        if multi:
+            dist.broadcast(yk, src=grid.rank_of(pk, qk))
+        B[:, k * nb:(k + 1) * nb] = yk
+    # ---- U x = y, block backward substitution along the block rows
+    for k in range(nblk - 1, -1, -1):
+        pk, qk = k % P, k % Q
+        s = torch.zeros((nrhs, nb), dtype=dt, device=dev)
+        if p == pk:
+            lj0 = _count_le(k, q, Q)                       # my block columns J > k of block row k
+            if lj0 * nb < nloc:
+                cols = torch.cat([torch.arange((lj * Q + q) * nb, (lj * Q + q + 1) * nb) for lj in range(lj0, nloc // nb)]).to(dev)
+                xr = B[:, cols].contiguous()
+                lkr = k // P
+                ops.gemm("N", nb, nrhs, cols.numel(), 1.0, U_loc[lj0 * nb:, lkr * nb:(lkr + 1) * nb], xr, 0.0, s)
+        if multi:
+            dist.all_reduce(s)
+        xk = (B[:, k * nb:(k + 1) * nb] - s).contiguous()
+        if p == pk and q == qk:
+            ops.trsm("U", "N", U_loc[(k // Q) * nb:(k // Q + 1) * nb, (k // P) * nb:(k // P + 1) * nb], xk)
+        if multi:
+            dist.broadcast(xk, src=grid.rank_of(pk, qk))
+        B[:, k * nb:(k + 1) * nb] = xk
+    return B

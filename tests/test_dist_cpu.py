@@ -42,3 +42,53 @@ def test_summa_block_cyclic_two_ranks(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+CHOL_SCRIPT = """
+import sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from lla_b200 import dist as LD
+dist.init_process_group("gloo")
+world, rank = dist.get_world_size(), dist.get_rank()
+ops = LD.TorchOps()
+for (P, Q) in ((1, 2), (2, 1)):
+    grid = LD.make_grid(P, Q)
+    nb = 3
+    n = nb * P * Q * 4
+    torch.manual_seed(1)
+    G = torch.rand((n, n), dtype=torch.float64)
+    S = G @ G.t() + n * torch.eye(n, dtype=torch.float64)
+    # what LLA hands to POTRF('U'): only the upper triangle of the column-major view is meaningful
+    full = torch.triu(S) + torch.tril(torch.full((n, n), 777.0, dtype=torch.float64), -1)
+    lay = LD.BlockCyclic(n, n, nb, grid)
+    A_loc = lay.scatter_from_global(full.t().contiguous())
+    info = LD.pdpotrf(grid, n, nb, A_loc, ops)
+    assert info == 0
+    out = lay.gather_to_global(A_loc).t()
+    U = torch.triu(out)
+    want = torch.linalg.cholesky(S).t()
+    assert torch.allclose(U, want, atol=1e-11), (P, Q, (U - want).abs().max())
+    assert torch.equal(torch.tril(out, -1), torch.tril(full, -1)), "lower triangle must not be touched"
+    # solve with the distributed factor, right-hand sides replicated
+    b = torch.rand((n, 5), dtype=torch.float64)
+    B = b.t().contiguous().clone()
+    LD.pdpotrs(grid, n, nb, A_loc, B, ops)
+    assert torch.allclose(S @ B.t(), b, atol=1e-10), (P, Q)
+    # not positive definite: INFO = index of the first failing leading minor, the same on every rank
+    bad = S.clone(); kbad = nb * 2 + 1; bad[kbad, kbad] = -1.0
+    A_loc = lay.scatter_from_global(bad.t().contiguous())
+    info = LD.pdpotrf(grid, n, nb, A_loc, ops)
+    assert info == kbad + 1, (info, kbad + 1)
+dist.destroy_process_group()
+"""
+
+
+def test_block_cyclic_cholesky_two_ranks(tmp_path):
+    script = tmp_path / "pchol.py"
+    script.write_text(CHOL_SCRIPT.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
