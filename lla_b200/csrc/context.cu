@@ -115,6 +115,10 @@ void trace_mark(cudaStream_t st, const char* label, long long a, long long b) {
   g_trace.push_back(r);
 }
 
+static const RowsFinalHook* g_rows_hook = nullptr;
+void set_rows_final_hook(const RowsFinalHook* h) { g_rows_hook = h; }
+const RowsFinalHook* rows_final_hook() { return g_rows_hook; }
+
 int DevBuf::alloc(size_t n) {
   if (n == 0) n = 16;
   cudaError_t e = cudaMalloc(&p, n);

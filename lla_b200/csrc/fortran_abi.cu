@@ -142,6 +142,56 @@ LLA_EXPORT void llacuda_dgemm(const char* transa, const char* transb, const int*
 // ------------------------------------------------------------------ LAPACK drop-ins
 static inline int64_t max1(int64_t x) { return x > 1 ? x : 1; }
 
+// Finished block rows of a factor go back to the caller while the factorisation is still running
+// (RowsFinalHook of the blocked drivers).  Only for page-locked host memory: a D2H copy into pageable
+// memory blocks the calling thread, which would stall the kernel queue of the following steps.
+struct RowSender {
+  const Staged* s;
+  double* host;
+  int64_t ldh;
+  cudaStream_t sd;
+  bool from_diagonal;     // Cholesky 'U': only columns >= r0 carry the factor
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int64_t sent_upto = 0;  // rows [0, sent_upto) are on their way
+  RowsFinalHook hook;
+  bool armed = false;
+  int arm(const Staged& st, double* h, int64_t ld, cudaStream_t d2h, bool diag) {
+    s = &st; host = h; ldh = ld; sd = d2h; from_diagonal = diag;
+    if (!host_is_pinned(h)) return 0;
+    for (auto& e : ev) LLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    hook.fn = &RowSender::rows_final; hook.user = this;
+    set_rows_final_hook(&hook);
+    armed = true;
+    return 0;
+  }
+  static int rows_final(void* user, int64_t r0, int64_t r1, cudaStream_t a, cudaStream_t b) {
+    RowSender* self = (RowSender*)user;
+    // rows are reported in order (and on the 512 grid of the triangle upload); anything else is left to the final copy
+    if (r0 != self->sent_upto || (self->from_diagonal && r0 % 512 != 0)) return 0;
+    LLA_CUDA(cudaEventRecord(self->ev[0], a));
+    LLA_CUDA(cudaStreamWaitEvent(self->sd, self->ev[0], 0));
+    if (b) {
+      LLA_CUDA(cudaEventRecord(self->ev[1], b));
+      LLA_CUDA(cudaStreamWaitEvent(self->sd, self->ev[1], 0));
+    }
+    if (self->from_diagonal) {
+      // the device holds exactly the trapezoids stage_upload_tri sent (512-column chunks, rows up to the chunk's
+      // end): walk the block row in the same 512 grid so that no byte outside them is written back
+      for (int64_t a = r0; a < r1; a += 512)
+        LLA_TRY(stage_download_rows(*self->s, self->host, self->ldh, a, a + 512 < r1 ? a + 512 : r1, a, self->sd));
+    } else {
+      LLA_TRY(stage_download_rows(*self->s, self->host, self->ldh, r0, r1, 0, self->sd));
+    }
+    self->sent_upto = r1;
+    return 0;
+  }
+  void disarm() { if (armed) set_rows_final_hook(nullptr); }
+  ~RowSender() {
+    disarm();
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+};
+
 // reads the device INFO word back; a CUDA failure overrides it with the out-of-band code
 
 static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, int* ipiv, int* info) {
@@ -158,9 +208,14 @@ static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, int* ipiv, 
   LLA_TRY(inf.alloc(sizeof(int)));
   LLA_TRY(stage_upload(sa, a, lda, st));
   tm.mark(1);
-  LLA_TRY(dgetrf_dev(m, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st));
+  RowSender rs;
+  LLA_TRY(rs.arm(sa, a, lda, cx->d2h, false));
+  int rc = dgetrf_dev(m, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st);
+  rs.disarm();
+  LLA_TRY(rc);
   tm.mark(2);
-  LLA_TRY(stage_download(sa, a, lda, st));
+  LLA_TRY(stage_download_rows(sa, a, lda, rs.sent_upto, m, 0, st));
+  LLA_CUDA(cudaStreamSynchronize(cx->d2h));
   if (mn > 0) LLA_CUDA(cudaMemcpyAsync(ipiv, piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
   LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
@@ -238,12 +293,17 @@ static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, int* ipiv
   LLA_TRY(stage_upload(sa, a, lda, st));
   LLA_TRY(stage_upload(sb, b, ldb, st));
   tm.mark(1);
-  LLA_TRY(dgetrf_dev(n, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st));
+  RowSender rs;
+  LLA_TRY(rs.arm(sa, a, lda, cx->d2h, false));
+  int rc = dgetrf_dev(n, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st);
+  rs.disarm();
+  LLA_TRY(rc);
   // DGESV solves only when the factorisation reported INFO = 0: the INFO word is the abort flag
   LLA_TRY(dgetrs_dev(0, n, nrhs, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st,
                      (const int*)inf.p));
   tm.mark(2);
-  LLA_TRY(stage_download(sa, a, lda, st));
+  LLA_TRY(stage_download_rows(sa, a, lda, rs.sent_upto, n, 0, st));
+  LLA_CUDA(cudaStreamSynchronize(cx->d2h));
   LLA_TRY(stage_download(sb, b, ldb, st));
   LLA_CUDA(cudaMemcpyAsync(ipiv, piv.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -277,13 +337,18 @@ static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, int* info)
   PoolBuf inf;
   LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
   LLA_TRY(inf.alloc(sizeof(int)));
-  LLA_TRY(stage_upload(sa, a, lda, st));
+  // only the named triangle crosses PCIe, in both directions: the other one is neither read nor written
+  // (LAPACK: "not referenced"), so the caller's bytes there stay as they are
+  LLA_TRY(stage_upload_tri(sa, a, lda, upper, st));
   tm.mark(1);
-  LLA_TRY(dpotrf_dev(upper, n, sa.ptr<double>(), sa.ld, (int*)inf.p, st));
+  RowSender rs;
+  if (upper) LLA_TRY(rs.arm(sa, a, lda, cx->d2h, true));
+  int rc = dpotrf_dev(upper, n, sa.ptr<double>(), sa.ld, (int*)inf.p, st);
+  rs.disarm();
+  LLA_TRY(rc);
   tm.mark(2);
-  // the other triangle is never written on the device, so copying the whole block back
-  // leaves the caller's bytes there unchanged
-  LLA_TRY(stage_download(sa, a, lda, st));
+  LLA_TRY(stage_download_tri(sa, a, lda, upper, rs.sent_upto, st));
+  LLA_CUDA(cudaStreamSynchronize(cx->d2h));
   LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   LLA_CUDA(cudaStreamSynchronize(st));

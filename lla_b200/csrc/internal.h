@@ -109,6 +109,15 @@ int dtrsm_left_inv_dev(bool upper, int op, int64_t m, int64_t n, const double* T
 inline size_t tinv_bytes(int64_t m) { return (size_t)((m + IB - 1) / IB) * IB * IB * sizeof(double); }
 
 // ------------------------------------------------------------------ factorisations
+// Optional per-call hook of the blocked drivers: rows [r0, r1) of the factor are final once the work queued so
+// far on streams `a` and `b` (b may be null) has completed.  The host-pointer entry points use it to send
+// finished block rows back over PCIe while the factorisation is still running.
+struct RowsFinalHook {
+  int (*fn)(void* user, int64_t r0, int64_t r1, cudaStream_t a, cudaStream_t b);
+  void* user;
+};
+void set_rows_final_hook(const RowsFinalHook* h);   // nullptr clears; valid for the next dgetrf_dev / dpotrf_dev only
+const RowsFinalHook* rows_final_hook();
 int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st);
 // rows i in [k1,k2) swapped with ipiv[i]-1 (1-based LAPACK pivots), forward or backward order
 int dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv,

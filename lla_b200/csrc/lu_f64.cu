@@ -557,6 +557,9 @@ static int lu_blocked(LuCtx L) {
     trace_mark(s1, "lu.updB<", k, L.N - c1);
     LLA_CUDA(cudaEventRecord(ev_b, s1));
     have_b = true;
+    // rows [k, k+kb) are final: U12 was solved at the head of this update, the L part received its last
+    // interchanges from this panel (later panels only touch rows below)
+    if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, s1, k > 0 ? s3 : nullptr));
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   if (mn > NB) LLA_CUDA(cudaStreamWaitEvent(s1, ev_left, 0));

@@ -110,6 +110,7 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, s2, info));
     trace_mark(s2, "chol.panel<", k, kb);
     LLA_CUDA(cudaEventRecord(ev_panel, s2));
+    if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, s2, nullptr));  // block row k of U is final
     if (n2 <= 0) break;
     // ---- trailing update of step k on s1
     LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));

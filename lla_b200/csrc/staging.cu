@@ -99,6 +99,47 @@ int stage_download_cols(const Staged& s, void* host, int64_t ldh, int64_t c0, in
   return 0;
 }
 
+int stage_upload_tri(Staged& s, const void* host, int64_t ldh, bool upper, cudaStream_t st, int64_t chunk) {
+  for (int64_t c0 = 0; c0 < s.cols; c0 += chunk) {
+    const int64_t c1 = c0 + chunk < s.cols ? c0 + chunk : s.cols;
+    const int64_t r0 = upper ? 0 : c0, r1 = upper ? (c1 < s.rows ? c1 : s.rows) : s.rows;
+    if (r1 <= r0) continue;
+    LLA_CUDA(cudaMemcpy2DAsync((char*)s.buf.p + ((size_t)c0 * s.ld + r0) * s.es, (size_t)s.ld * s.es,
+                               (const char*)host + ((size_t)c0 * ldh + r0) * s.es, (size_t)ldh * s.es,
+                               (size_t)(r1 - r0) * s.es, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+  }
+  return 0;
+}
+
+// triangle restricted to rows >= r0 (the rows above were already sent back by the rows-final hook)
+int stage_download_tri(const Staged& s, void* host, int64_t ldh, bool upper, int64_t r0, cudaStream_t st, int64_t chunk) {
+  for (int64_t c0 = 0; c0 < s.cols; c0 += chunk) {
+    const int64_t c1 = c0 + chunk < s.cols ? c0 + chunk : s.cols;
+    int64_t a = upper ? 0 : c0, b = upper ? (c1 < s.rows ? c1 : s.rows) : s.rows;
+    if (a < r0) a = r0;
+    if (b <= a) continue;
+    LLA_CUDA(cudaMemcpy2DAsync((char*)host + ((size_t)c0 * ldh + a) * s.es, (size_t)ldh * s.es,
+                               (const char*)s.buf.p + ((size_t)c0 * s.ld + a) * s.es, (size_t)s.ld * s.es,
+                               (size_t)(b - a) * s.es, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
+  }
+  return 0;
+}
+
+int stage_download_rows(const Staged& s, void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, cudaStream_t st) {
+  if (r1 <= r0 || c0 >= s.cols) return 0;
+  LLA_CUDA(cudaMemcpy2DAsync((char*)host + ((size_t)c0 * ldh + r0) * s.es, (size_t)ldh * s.es,
+                             (const char*)s.buf.p + ((size_t)c0 * s.ld + r0) * s.es, (size_t)s.ld * s.es,
+                             (size_t)(r1 - r0) * s.es, (size_t)(s.cols - c0), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory: only then is a D2H copy asynchronous to the host
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 PhaseTimer::PhaseTimer(cudaStream_t s) : st(s) {
   ok = true;
   for (auto& x : e)

@@ -30,8 +30,13 @@ struct Staged {
 
 int stage_alloc(Staged& s, int64_t rows, int64_t cols, size_t es);
 int stage_upload(Staged& s, const void* host, int64_t ldh, cudaStream_t st);
-// upload only the part of the matrix selected by tri (0 all, 1 upper incl. diagonal, 2 lower)
 int stage_download(const Staged& s, void* host, int64_t ldh, cudaStream_t st);
+// only the named triangle (incl. diagonal) of a square matrix, as trapezoids of `chunk` columns
+int stage_upload_tri(Staged& s, const void* host, int64_t ldh, bool upper, cudaStream_t st, int64_t chunk = 512);
+int stage_download_tri(const Staged& s, void* host, int64_t ldh, bool upper, int64_t r0, cudaStream_t st, int64_t chunk = 512);
+// rows [r0, r1) of the columns [c0, cols)
+int stage_download_rows(const Staged& s, void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, cudaStream_t st);
+bool host_is_pinned(const void* p);
 // column range [c0, c1) only
 int stage_upload_cols(Staged& s, const void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st);
 int stage_download_cols(const Staged& s, void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st);

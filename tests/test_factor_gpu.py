@@ -238,3 +238,69 @@ def test_solve_large_residual():
     x = L.solve(a, b)
     assert residual(a, x, b) <= 10
     assert np.allclose(x, O.solve(a, b, O.openblas()), rtol=1e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------ page-locked host operands: the Fortran drop-ins
+# send finished block rows back while the factorisation is still running (RowsFinalHook) and move only the
+# named triangle for DPOTRF; the results must be the bytes the plain (pageable) path produces.
+def _pinned_like(a):
+    import ctypes
+    from lla_b200 import _lib
+    lib = _lib.lib()
+    p = ctypes.c_void_p()
+    lib.llacuda_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    assert lib.llacuda_host_alloc(ctypes.byref(p), a.nbytes) == 0
+    buf = np.ctypeslib.as_array((ctypes.c_char * a.nbytes).from_address(p.value)).view(a.dtype).reshape(a.shape)
+    buf[...] = a
+    return buf, p
+
+
+@pytest.mark.parametrize("n", [1536, 2100])
+def test_pinned_host_overlapped_downloads_match_pageable(n):
+    import ctypes
+    from lla_b200 import _lib
+    lib = _lib.lib()
+    I = lambda v: ctypes.byref(ctypes.c_int(v))
+    P = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(n)
+    # ---- dgetrf_ / dgesv_ (column-major images)
+    a = np.asfortranarray(rng.uniform(0, 10, (n, n)))
+    b = np.asfortranarray(rng.uniform(0, 10, (n, 3)))
+    outs = []
+    for pinned in (False, True):
+        aa, bb = a.copy(order="F"), b.copy(order="F")
+        keep = []
+        if pinned:
+            aa_, h1 = _pinned_like(aa.T); bb_, h2 = _pinned_like(bb.T); keep = [h1, h2]   # .T of F-order = C-order bytes
+            aw, bw = aa_, bb_
+        else:
+            aw, bw = np.ascontiguousarray(aa.T), np.ascontiguousarray(bb.T)
+        ipiv = np.zeros(n, dtype=np.int32); info = ctypes.c_int(0)
+        lib.dgesv_(I(n), I(3), P(aw), I(n), P(ipiv), P(bw), I(n), ctypes.byref(info))
+        assert info.value == 0
+        outs.append((aw.copy(), bw.copy(), ipiv.copy()))
+        for h in keep:
+            lib.llacuda_host_free(h)
+    assert np.array_equal(outs[0][2], outs[1][2])
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert residual(a, outs[1][1].T, b) <= 10
+    # ---- dpotrf_ 'U': only the upper triangle of the column-major view is read or written
+    spd = a @ a.T + n * np.eye(n)
+    img = np.ascontiguousarray(np.triu(spd).T)            # column-major image, lower triangle of the view = sentinel
+    img[np.triu_indices(n, 1)] = -777.0                   # image[c, r] with c < r  <=>  matrix (r, c) below the diagonal
+    res = []
+    for pinned in (False, True):
+        if pinned:
+            w, h = _pinned_like(img)
+        else:
+            w, h = img.copy(), None
+        info = ctypes.c_int(0)
+        lib.dpotrf_(ctypes.c_char_p(b"U"), I(n), P(w), I(n), ctypes.byref(info))
+        assert info.value == 0
+        res.append(w.copy())
+        if h is not None:
+            lib.llacuda_host_free(h)
+    assert np.array_equal(res[0], res[1])
+    u = np.triu(res[1].T)
+    assert np.all(res[1][np.triu_indices(n, 1)] == -777.0), "the other triangle must come back untouched"
+    assert np.linalg.norm(u.T @ u - spd) / (n * EPS * np.linalg.norm(spd)) <= 10
