@@ -316,8 +316,10 @@ def gpu_legs(args, rank, world, local_rank):
         tt = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_total = float(tt.item())
-    h2d = 2 * n * n * 8 + (n * n * 8 + n * nrhs * 8) + n * n * 8
-    d2h = n * n * 8 + (n * n * 8 + n * nrhs * 8 + n * 4 + 4) + (n * n * 8 + 4)
+    # dpotrf_ moves only the upper triangle, as 512-column trapezoids (csrc/staging.cu: stage_upload_tri)
+    tri = sum(min(c0 + 512, n) * (min(c0 + 512, n) - c0) for c0 in range(0, n, 512)) * 8
+    h2d = 2 * n * n * 8 + (n * n * 8 + n * nrhs * 8) + tri
+    d2h = n * n * 8 + (n * n * 8 + n * nrhs * 8 + n * 4 + 4) + (tri + 4)
     res["e2e"] = {"value": world * sum(f.values()) * e2e_steps / e2e_total / 1e9, "unit": "GFLOP/s",
                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                   "ops": {k: f[k] * e2e_steps / te[k] / 1e9 for k in te}, "host_memory": "pinned (llacuda_host_alloc)"}
