@@ -104,6 +104,9 @@ int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const double* A, int6
  * (reference src/linear-algebra.lisp:333-347); used by the block-cyclic factorisations. */
 int llacuda_dtrsm_dev(char uplo, char trans, char diag, int64_t m, int64_t n, const double* T, int64_t ldt,
                       double* B, int64_t ldb);
+/* rows i <-> ipiv[i]-1 for i in [k1, k2) (0-based i, 1-based LAPACK pivots) on ncols columns, forward or reverse
+ * order: the DLASWP step of GETRF/GETRS (reference call sites src/linear-algebra.lisp:227-234, 269-276). */
+int llacuda_dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv_dev, int forward);
 int llacuda_dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t strideA, int* ipiv_dev,
                               double* B, int64_t strideB, int* info_dev, int keep_lu);
 /* out[c + r*ldout] = in[r + c*ldin]: the device-side replacement of LLA's

@@ -620,3 +620,15 @@ int dgetrs_dev(int op, int64_t n, int64_t nrhs, const double* A, int64_t lda, co
 }
 
 }  // namespace llacuda
+
+using namespace llacuda;
+
+// Row interchanges i <-> ipiv[i]-1, i in [k1, k2), on the ncols columns of A (DLASWP with incx = +-1): what the
+// processes of the block-cyclic LU (lla_b200/dist.py) apply to their own columns after a panel's pivots arrive.
+extern "C" int llacuda_dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv_dev,
+                                  int forward) {
+  Context* c = ctx();
+  if (!c) return LLACUDA_ERR_NO_DEVICE;
+  if (ncols < 0 || k1 < 0 || k2 < k1 || lda < 1) return LLACUDA_ERR_BAD_ARG;
+  return dlaswp_dev(ncols, A, lda, k1, k2, ipiv_dev, forward != 0, c->stream);
+}

@@ -77,6 +77,11 @@ def dtrsm(uplo, trans, diag, m, n, T, ldt, B, ldb):
     _lib.check(f(uplo.encode(), trans.encode(), diag.encode(), m, n, T, ldt, B, ldb), "dtrsm_dev")
 
 
+def dlaswp(ncols, A, lda, k1, k2, ipiv, forward=True):
+    f = _sig("llacuda_dlaswp_dev", [_i64, _vp, _i64, _i64, _i64, _ip, ctypes.c_int])
+    _lib.check(f(ncols, A, lda, k1, k2, ipiv, 1 if forward else 0), "dlaswp_dev")
+
+
 def dtranspose(rows, cols, src, ldin, dst, ldout):
     f = _sig("llacuda_dtranspose_dev", [_i64, _i64, _vp, _i64, _vp, _i64])
     _lib.check(f(rows, cols, src, ldin, dst, ldout), "dtranspose_dev")

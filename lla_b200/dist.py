@@ -185,9 +185,22 @@ class DeviceOps:
         self.D.dpotrf("U", n, img.data_ptr(), self._ld(img), self._info.data_ptr())
         return self._info   # device scalar; the caller decides when to read it
 
-    def trsm(self, uplo, trans, timg, bimg):
+    def trsm(self, uplo, trans, timg, bimg, diag="N"):
         m, n = bimg.shape[1], bimg.shape[0]
-        self.D.dtrsm(uplo, trans, "N", m, n, timg.data_ptr(), self._ld(timg), bimg.data_ptr(), self._ld(bimg))
+        self.D.dtrsm(uplo, trans, diag, m, n, timg.data_ptr(), self._ld(timg), bimg.data_ptr(), self._ld(bimg))
+
+    def getrf(self, img, ipiv):
+        """LU with partial pivoting of the (rows x cols) panel behind the (cols, rows) image; ipiv: int32 device
+        tensor (1-based, relative to the panel's first row).  Returns the device INFO scalar."""
+        if self._info is None:
+            self._info = torch.zeros(1, dtype=torch.int32, device=img.device)
+        self.D.dgetrf(img.shape[1], img.shape[0], img.data_ptr(), self._ld(img), ipiv.data_ptr(), self._info.data_ptr())
+        return self._info
+
+    def laswp(self, img, ipiv, forward=True):
+        """rows i <-> ipiv[i]-1, i in [0, len(ipiv)), on all columns of the image."""
+        if img.shape[0] > 0:
+            self.D.dlaswp(img.shape[0], img.data_ptr(), self._ld(img), 0, ipiv.numel(), ipiv.data_ptr(), forward)
 
     def gemm(self, opa, m, n, k, alpha, aimg, bimg, beta, cimg, tri=0):
         """C (m x n) = alpha op(A) B + beta C, op = 'T' or 'N'; tri: 0 full, 1 upper, 2 lower."""
@@ -205,9 +218,26 @@ class TorchOps:
         a.copy_(torch.triu(l.t()) + torch.tril(a, -1))  # only the upper triangle is written
         return info.to(torch.int32).reshape(1)
 
-    def trsm(self, uplo, trans, timg, bimg):
+    def getrf(self, img, ipiv):
+        a = img.t()
+        lu, piv, info = torch.linalg.lu_factor_ex(a.contiguous())
+        a.copy_(lu)
+        ipiv.copy_(piv[:ipiv.numel()].to(torch.int32))
+        return info.to(torch.int32).reshape(1)
+
+    def laswp(self, img, ipiv, forward=True):
+        a = img.t()
+        order = range(ipiv.numel()) if forward else range(ipiv.numel() - 1, -1, -1)
+        for i in order:
+            pi = int(ipiv[i]) - 1
+            if pi != i:
+                tmp = a[i].clone(); a[i] = a[pi]; a[pi] = tmp
+
+    def trsm(self, uplo, trans, timg, bimg, diag="N"):
         t = timg.t()
         t = torch.triu(t) if uplo == "U" else torch.tril(t)
+        if diag == "U":
+            t = t - torch.diag(torch.diagonal(t)) + torch.eye(t.shape[0], dtype=t.dtype)
         if trans == "T":
             x = torch.linalg.solve_triangular(t.t(), bimg.t(), upper=(uplo != "U"))
         else:
@@ -418,4 +448,150 @@ def pdpotrs(grid: Grid, n, nb, U_loc, B, ops=None):
         if multi:
             dist.broadcast(xk, src=grid.rank_of(pk, qk))
         B[:, k * nb:(k + 1) * nb] = xk
+    return B
+
+
+# --------------------------------------------------------------------------------------------------
+# Block-cyclic LU with partial pivoting on a 1 x Q grid: block column J lives on
+# process J mod Q with all of its rows, so a panel's pivot search never leaves the GPU that owns it --
+# the panel is factored by the very kernel the single-GPU DGETRF uses, on the same numbers in the same
+# order, which is what keeps ipiv bit-exact for every GPU count.  Per block step k:
+#   1. the owner factors its m_k x nb panel (DGETRF) and broadcasts the panel and its pivots (NCCL over
+#      NVLink: m_k x nb doubles per step);
+#   2. every process applies the interchanges to its own block columns (left and right of the panel),
+#      solves U_kJ = L_kk^-1 A_kJ and updates A_IJ -= L_Ik U_kJ with the DMMA GEMM;
+# with `lookahead` the owner of panel k+1 updates that block column first and factors it on a second
+# stream while everybody's remaining update of step k is still running.
+
+def _one_row_grid(grid):
+    if grid.P != 1:
+        raise ValueError("pdgetrf distributes block columns: use a 1 x Q grid (make_grid(1, world))")
+
+
+def pdgetrf(grid: Grid, n, nb, A_loc, ipiv, ops=None, lookahead=True):
+    """In-place LU of the n x n matrix held as local block columns A_loc ((n/Q, n) column-major image);
+    ipiv: int32 tensor of length n on every rank (LAPACK's 1-based swap sequence on return).
+    Returns LAPACK's INFO (0 or the index of the first exactly-zero pivot; the factorisation completes)."""
+    _one_row_grid(grid)
+    ops = ops or DeviceOps()
+    Q, q = grid.Q, grid.q
+    nloc = n // Q
+    assert A_loc.shape == (nloc, n) and n % (nb * Q) == 0
+    nblk = n // nb
+    dev, dt = A_loc.device, A_loc.dtype
+    cuda = dev.type == "cuda"
+    multi = Q > 1
+    info_acc = torch.zeros(1, dtype=torch.int32, device=dev)
+    lbuf = [torch.empty(nb * n, dtype=dt, device=dev) for _ in range(2)]         # panel k: contiguous (nb, n - k nb) image
+    pbuf = [torch.empty(nb, dtype=torch.int32, device=dev) for _ in range(2)]
+    main = torch.cuda.current_stream() if cuda else None
+    side = torch.cuda.Stream(priority=-1) if (cuda and lookahead) else main
+    ev_panel = [torch.cuda.Event() for _ in range(2)] if cuda else None
+    ev_col = torch.cuda.Event() if cuda else None
+
+    class _on:
+        def __init__(self, stream): self.stream = stream
+        def __enter__(self):
+            if cuda:
+                self.ctx = torch.cuda.stream(self.stream); self.ctx.__enter__()
+                if hasattr(ops, "D"): ops.D.use_torch_stream()
+        def __exit__(self, *a):
+            if cuda:
+                self.ctx.__exit__(*a)
+                if hasattr(ops, "D"): ops.D.use_torch_stream()
+
+    def panel(k):
+        nonlocal info_acc
+        r0 = k * nb
+        pan = lbuf[k % 2][:nb * (n - r0)].view(nb, n - r0)
+        piv = pbuf[k % 2]
+        if q == k % Q:
+            lk = k // Q
+            mine = A_loc[lk * nb:(lk + 1) * nb, r0:]
+            inf = ops.getrf(mine, piv)
+            info_acc += torch.where((info_acc == 0) & (inf != 0), inf + r0, torch.zeros_like(inf))
+            pan.copy_(mine)
+        if multi:
+            dist.broadcast(pan, src=k % Q)
+            dist.broadcast(piv, src=k % Q)
+        return pan, piv
+
+    def update(k, pan, piv, lj_lo, lj_hi):
+        """interchanges + U_kJ + trailing update on my local block columns [lj_lo, lj_hi) (all right of panel k)."""
+        if lj_hi <= lj_lo:
+            return
+        r0 = k * nb
+        cols = A_loc[lj_lo * nb:lj_hi * nb, r0:]                  # image of the rows >= r0 of those columns
+        ops.laswp(cols, piv, True)
+        ops.trsm("L", "N", pan[:, :nb], cols[:, :nb], diag="U")
+        m2 = n - r0 - nb
+        if m2 > 0:
+            ops.gemm("N", m2, cols.shape[0], nb, -1.0, pan[:, nb:], cols[:, :nb], 1.0, cols[:, nb:])
+
+    with _on(side):
+        nxt = panel(0)
+        if cuda: ev_panel[0].record(side)
+    for k in range(nblk):
+        pan, piv = nxt
+        if cuda and side is not main: main.wait_event(ev_panel[k % 2])
+        ipiv[k * nb:(k + 1) * nb] = piv + k * nb
+        lj0 = _count_le(k, q, Q)                                  # my first block column right of panel k
+        # interchanges of my block columns left of the panel (nothing depends on them until the end)
+        nleft = _count_le(k - 1, q, Q)
+        if nleft > 0:
+            ops.laswp(A_loc[:nleft * nb, k * nb:], piv, True)
+        own_next = (k + 1 < nblk) and ((k + 1) % Q == q)
+        split = lj0 + 1 if own_next else lj0
+        if own_next:
+            update(k, pan, piv, lj0, split)                        # block column k+1 first
+        if k + 1 < nblk:
+            if cuda and side is not main:
+                ev_col.record(main); side.wait_event(ev_col)
+            with _on(side):
+                nxt = panel(k + 1)
+                if cuda: ev_panel[(k + 1) % 2].record(side)
+        update(k, pan, piv, split, nloc // nb)
+    if cuda and side is not main: main.wait_stream(side)
+    if multi:
+        big = torch.where(info_acc > 0, info_acc, torch.full_like(info_acc, 2 ** 31 - 1))
+        dist.all_reduce(big, op=dist.ReduceOp.MIN)
+        info_acc = torch.where(big == 2 ** 31 - 1, torch.zeros_like(big), big)
+    return int(info_acc.item())
+
+
+def pdgetrs(grid: Grid, n, nb, LU_loc, ipiv, B, ops=None):
+    """Solves A X = B in place with the factors of pdgetrf; B is replicated on every rank as the (nrhs, n)
+    column-major image of the right-hand sides.  Column-oriented substitution: the owner of block column k
+    holds all of L(:, k) and U(:, k), so it solves its block and folds it into the rest, then broadcasts."""
+    _one_row_grid(grid)
+    ops = ops or DeviceOps()
+    Q, q = grid.Q, grid.q
+    nblk = n // nb
+    nrhs = B.shape[0]
+    multi = Q > 1
+    ops.laswp(B, ipiv, True)
+    for k in range(nblk):                                          # L y = P b
+        r0 = k * nb
+        tail = B[:, r0:].contiguous()
+        if q == k % Q:
+            lk = k // Q
+            col = LU_loc[lk * nb:(lk + 1) * nb, r0:]
+            ops.trsm("L", "N", col[:, :nb], tail[:, :nb], diag="U")
+            if n - r0 - nb > 0:
+                ops.gemm("N", n - r0 - nb, nrhs, nb, -1.0, col[:, nb:], tail[:, :nb], 1.0, tail[:, nb:])
+        if multi:
+            dist.broadcast(tail, src=k % Q)
+        B[:, r0:] = tail
+    for k in range(nblk - 1, -1, -1):                              # U x = y
+        r1 = (k + 1) * nb
+        head = B[:, :r1].contiguous()
+        if q == k % Q:
+            lk = k // Q
+            col = LU_loc[lk * nb:(lk + 1) * nb, :r1]
+            ops.trsm("U", "N", col[:, r1 - nb:], head[:, r1 - nb:])
+            if r1 - nb > 0:
+                ops.gemm("N", r1 - nb, nrhs, nb, -1.0, col[:, :r1 - nb], head[:, r1 - nb:], 1.0, head[:, :r1 - nb])
+        if multi:
+            dist.broadcast(head, src=k % Q)
+        B[:, :r1] = head
     return B

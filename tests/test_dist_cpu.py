@@ -92,3 +92,54 @@ def test_block_cyclic_cholesky_two_ranks(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+LU_SCRIPT = """
+import sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from lla_b200 import dist as LD
+dist.init_process_group("gloo")
+world, rank = dist.get_world_size(), dist.get_rank()
+ops = LD.TorchOps()
+grid = LD.make_grid(1, 2)
+nb = 3
+n = nb * 2 * 4
+torch.manual_seed(2)
+M = torch.rand((n, n), dtype=torch.float64) * 10            # as lu-random-test, tests/linear-algebra.lisp:112
+lay = LD.BlockCyclic(n, n, nb, grid)
+want_lu, want_piv = torch.linalg.lu_factor(M)
+for look in (True, False):
+    A_loc = lay.scatter_from_global(M.t().contiguous())
+    ipiv = torch.zeros(n, dtype=torch.int32)
+    info = LD.pdgetrf(grid, n, nb, A_loc, ipiv, ops, lookahead=look)
+    assert info == 0
+    assert torch.equal(ipiv, want_piv.to(torch.int32)), "ipiv must not depend on the process count"
+    got = lay.gather_to_global(A_loc).t()
+    assert torch.allclose(got, want_lu, atol=1e-11)
+    b = torch.rand((n, 5), dtype=torch.float64)
+    B = b.t().contiguous().clone()
+    LD.pdgetrs(grid, n, nb, A_loc, ipiv, B, ops)
+    assert torch.allclose(M @ B.t(), b, atol=1e-9)
+# exactly singular: INFO = first zero pivot, factorisation completes (lu-singular, tests/linear-algebra.lisp:106-107)
+S = M.clone(); S[:, 4] = 0.0
+A_loc = lay.scatter_from_global(S.t().contiguous())
+ipiv = torch.zeros(n, dtype=torch.int32)
+assert LD.pdgetrf(grid, n, nb, A_loc, ipiv, ops) == 5
+try:
+    LD.pdgetrf(LD.make_grid(2, 1), n, nb, A_loc, ipiv, ops)
+    raise SystemExit("a 2 x 1 grid must be refused")
+except ValueError:
+    pass
+dist.destroy_process_group()
+"""
+
+
+def test_block_column_lu_two_ranks(tmp_path):
+    script = tmp_path / "plu.py"
+    script.write_text(LU_SCRIPT.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29545", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
