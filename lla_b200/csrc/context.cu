@@ -115,6 +115,26 @@ void trace_mark(cudaStream_t st, const char* label, long long a, long long b) {
   g_trace.push_back(r);
 }
 
+struct StreamBuf { void* p; size_t bytes; };
+static std::vector<std::pair<cudaStream_t, StreamBuf>> g_stream_scratch;
+void* stream_scratch(cudaStream_t st, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& e : g_stream_scratch) {
+    if (e.first != st) continue;
+    if (e.second.bytes >= bytes) return e.second.p;
+    cudaStreamSynchronize(st);   // the only user of this buffer is work queued on st
+    cudaFree(e.second.p);
+    e.second = {nullptr, 0};
+    if (cudaMalloc(&e.second.p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    e.second.bytes = bytes;
+    return e.second.p;
+  }
+  StreamBuf b{nullptr, bytes};
+  if (cudaMalloc(&b.p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_stream_scratch.push_back({st, b});
+  return b.p;
+}
+
 static const RowsFinalHook* g_rows_hook = nullptr;
 void set_rows_final_hook(const RowsFinalHook* h) { g_rows_hook = h; }
 const RowsFinalHook* rows_final_hook() { return g_rows_hook; }

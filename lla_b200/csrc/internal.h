@@ -56,6 +56,11 @@ struct Arena {
   void* take(size_t bytes);
 };
 
+// Scratch that belongs to one stream (grow-only): for device entry points that may run concurrently with a
+// factorisation on another stream (the block-cyclic drivers of lla_b200/dist.py update on one stream while the
+// next panel is factored on a second one), where the shared per-call arena above must not be touched.
+void* stream_scratch(cudaStream_t st, size_t bytes);
+
 // number of llacuda kernels launched by this process (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 

@@ -208,9 +208,9 @@ extern "C" int llacuda_dtrsm_dev(char uplo, char trans, char diag, int64_t m, in
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   if (m == 0 || n == 0) return 0;
-  Arena ar;
-  LLA_TRY(ar.reserve(tinv_bytes(m) + 1024));
-  double* tinv = (double*)ar.take(tinv_bytes(m));
+  // per-stream scratch, not the shared arena: this entry point runs next to a factorisation on another stream
+  double* tinv = (double*)stream_scratch(c->stream, tinv_bytes(m));
+  if (!tinv) { set_error(__FILE__, __LINE__, "dtrsm: out of device memory for the block inverses", (int)m); return LLACUDA_ERR_CUDA_BASE; }
   LLA_TRY(dtrtri_blocks_dev(upper, unit, m, T, ldt, tinv, c->stream));
   return dtrsm_left_inv_dev(upper, op, m, n, T, ldt, tinv, B, ldb, c->stream);
 }

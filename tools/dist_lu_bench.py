@@ -23,12 +23,14 @@ grid = LD.make_grid(1, world)
 n, nb, Q = args.size, args.block, world
 lay = LD.BlockCyclic(n, n, nb, grid)
 
-def column(j):  # rank-independent synthetic column j (n values in [0, 10)), reproducible on any rank
-    g = torch.Generator(device=dev); g.manual_seed(1000003 * 7 + int(j))
-    return torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 10
+def elems(i, j):
+    # rank-independent synthetic entries in [0, 10): a hash of (i, j) evaluated in closed form on the device
+    x = torch.sin(i * 12.9898 + j * 78.233) * 43758.5453
+    return (x - torch.floor(x)) * 10.0
 
-cols = [J * nb + c for J in lay.local_block_cols() for c in range(nb)]
-A0 = torch.stack([column(j) for j in cols])                  # (nloc, n) image
+ii = torch.arange(n, device=dev, dtype=torch.float64)
+jloc = torch.cat([torch.arange(J * nb, (J + 1) * nb) for J in lay.local_block_cols()]).to(dev).double()
+A0 = elems(ii[None, :], jloc[:, None]).contiguous()          # (nloc, n) image
 A_loc = A0.clone()
 ipiv = torch.zeros(n, dtype=torch.int32, device=dev)
 x0 = torch.ones(n, dtype=torch.float64, device=dev)
@@ -54,7 +56,7 @@ ms_s = timed(lambda: LD.pdgetrs(grid, n, nb, A_loc, ipiv, B), lambda: B.copy_(B0
 err = (B - 1.0).abs().max(); dist.all_reduce(err, op=dist.ReduceOp.MAX)
 same = None
 if args.check and rank == 0 and n <= 32768:
-    full = torch.stack([column(j) for j in range(n)])
+    full = elems(ii[None, :], ii[:, None]).contiguous()
     ip1 = torch.zeros(n, dtype=torch.int32, device=dev); info1 = torch.zeros(1, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
