@@ -86,6 +86,10 @@ int llacuda_sgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, float
 int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
                       const void* A, int64_t lda, const void* B, int64_t ldb,
                       const double* beta2, void* C, int64_t ldc);
+/* complex single (interleaved re,im) on the tcgen05 SGEMM: planar split, four real products, complex combine */
+int llacuda_cgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const float* alpha2,
+                      const void* A, int64_t lda, const void* B, int64_t ldb,
+                      const float* beta2, void* C, int64_t ldc);
 /* factorisations and solves on device-resident column-major operands; ipiv_dev / info_dev are
  * DEVICE pointers (int32), written asynchronously on llacuda_stream() */
 int llacuda_dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv_dev, int* info_dev);
@@ -129,6 +133,12 @@ void sgemm_(const char* transa, const char* transb, const int* m, const int* n, 
 void llacuda_sgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
                    const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
                    const float* beta, float* c, const int* ldc);
+void cgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+            const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
+            const void* beta, void* c, const int* ldc);
+void llacuda_cgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
+                   const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
+                   const void* beta, void* c, const int* ldc);
 void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
             const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
             const void* beta, void* c, const int* ldc);

@@ -222,3 +222,35 @@ def test_gemm_degenerate_shapes():
     b = rng.uniform(-1, 1, (200, 1))
     assert np.allclose(L.mm(a, b), a @ b, atol=1e-13)
     assert np.allclose(L.mm(b, a), b @ a, atol=1e-13)
+
+
+# ------------------------------------------------------------------ complex single (planar split over the tcgen05 SGEMM)
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (5, 7, 3), (130, 70, 33), (257, 129, 100)])
+def test_cgemm_vs_oracle(ta, tb, m, n, k):
+    """gemm! on complex-single arrays (type letter c): a transposed operand is CONJUGATE-transposed."""
+    rng = np.random.default_rng(m * 100 + n * 10 + k + 5)
+    mk = lambda r, c: (rng.uniform(-1, 1, (r, c)) + 1j * rng.uniform(-1, 1, (r, c))).astype(np.complex64)
+    a = mk(*((k, m) if ta else (m, k)))
+    b = mk(*((n, k) if tb else (k, n)))
+    c = mk(m, n)
+    for alpha, beta in ((1.0 + 0j, 0j), (0.7 - 0.2j, 1.3 + 0.5j), (0j, 0.5 + 0.1j)):
+        got = L.gemm(np.complex64(alpha), a, b, np.complex64(beta), c.copy(), transpose_a=ta, transpose_b=tb)
+        assert got.dtype == np.complex64
+        opa = (a.conj().T if ta else a).astype(np.complex128)
+        opb = (b.conj().T if tb else b).astype(np.complex128)
+        want = alpha * (opa @ opb) + beta * c.astype(np.complex128)
+        host = O.gemm(np.complex64(alpha), a, b, np.complex64(beta), c.copy(), O.openblas(), transpose_a=ta, transpose_b=tb)
+        tol = 4 * sgemm_tol(np.abs(opa), np.abs(opb), k, abs(alpha)) + 8 * EPS32 * (abs(beta) * np.abs(c) + np.abs(want))
+        assert np.all(np.abs(got.astype(np.complex128) - want) <= tol), np.max(np.abs(got - want) / tol)
+        assert np.all(np.abs(got.astype(np.complex128) - host.astype(np.complex128)) <= 2 * tol)
+
+
+def test_cmm_types():
+    rng = np.random.default_rng(12)
+    a = (rng.uniform(-1, 1, (60, 40)) + 1j * rng.uniform(-1, 1, (60, 40))).astype(np.complex64)
+    b = rng.uniform(-1, 1, (40, 50)).astype(np.float32)      # single * complex-single -> complex-single
+    got = L.mm(a, b)
+    assert got.dtype == np.complex64
+    assert np.allclose(got, a.astype(np.complex128) @ b.astype(np.float64), atol=1e-4)
