@@ -306,6 +306,44 @@ __global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restr
 constexpr int SW_CHUNK = 32;
 constexpr int SW_COLS = 8;
 
+// One warp composes the interchanges [lo, hi) (at most 32, applied forward or in reverse) into one permutation
+// over the <= 64 touched rows: dst[s] receives the original content of row src[s] (-1 = unused slot).  Lane k
+// tracks slot k (row lo+k) and slot 32+k (k-th distinct row outside [lo, hi)).
+__device__ __forceinline__ void laswp_compose_chunk(int lane, int64_t lo, int64_t hi, bool forward,
+                                                    const int* __restrict__ ipiv, int* dst, int* src) {
+  const int cnt = (int)(hi - lo);
+  int row_a = (int)lo + lane, cur_a = row_a;  // rows of the chunk itself
+  int row_b = -1, cur_b = -1;                 // extra rows, filled in order of appearance
+  int nextra = 0;
+  for (int q = 0; q < cnt; q++) {
+    const int i = forward ? (int)lo + q : (int)hi - 1 - q;
+    const int p = ipiv[i] - 1;
+    if (p == i) continue;
+    const int ia = i - (int)lo;
+    int ip;  // slot index 0..63
+    if (p >= lo && p < hi) ip = p - (int)lo;
+    else {
+      unsigned hit = __ballot_sync(0xffffffffu, row_b == p);
+      if (hit) ip = 32 + (__ffs(hit) - 1);
+      else {
+        ip = 32 + nextra;
+        if (lane == nextra) { row_b = p; cur_b = p; }
+        nextra++;
+      }
+    }
+    // swap the contents of slots ia and ip
+    int ca = __shfl_sync(0xffffffffu, cur_a, ia);
+    int cp = (ip < 32) ? __shfl_sync(0xffffffffu, cur_a, ip) : __shfl_sync(0xffffffffu, cur_b, ip - 32);
+    if (lane == ia) cur_a = cp;
+    if (ip < 32) { if (lane == ip) cur_a = ca; }
+    else { if (lane == ip - 32) cur_b = ca; }
+  }
+  dst[lane] = (lane < cnt) ? row_a : -1;
+  src[lane] = (lane < cnt) ? cur_a : -1;
+  dst[32 + lane] = (lane < nextra) ? row_b : -1;
+  src[32 + lane] = (lane < nextra) ? cur_b : -1;
+}
+
 __global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) lla_dlaswp_kernel(double* __restrict__ A, int64_t lda, int64_t ncols,
                                                                        int64_t skip0, int64_t skip1, int64_t k1, int64_t k2,
                                                                        const int* __restrict__ ipiv, bool forward,
@@ -313,7 +351,6 @@ __global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) lla_dlaswp_kernel(doub
   if (abort_flag != nullptr && *abort_flag != 0) return;
   __shared__ int s_rows[2 * SW_CHUNK];  // touched rows (destinations)
   __shared__ int s_src[2 * SW_CHUNK];   // row whose original content ends up there
-  __shared__ int s_n;
   const int tid = threadIdx.x;
   const int s = tid % (2 * SW_CHUNK);
   const int cl = tid / (2 * SW_CHUNK);
@@ -327,43 +364,7 @@ __global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) lla_dlaswp_kernel(doub
     int64_t lo, hi;  // this chunk covers swaps [lo, hi)
     if (forward) { lo = k1 + ch * SW_CHUNK; hi = lo + SW_CHUNK < k2 ? lo + SW_CHUNK : k2; }
     else { hi = k2 - ch * SW_CHUNK; lo = hi - SW_CHUNK > k1 ? hi - SW_CHUNK : k1; }
-    const int cnt = (int)(hi - lo);
-    if (tid < 32) {
-      // lane k tracks slot k (row lo+k) and slot 32+k (k-th distinct outside row)
-      const int lane = tid;
-      int row_a = (int)lo + lane, cur_a = row_a;  // rows of the chunk itself
-      int row_b = -1, cur_b = -1;                 // extra rows, filled in order of appearance
-      int nextra = 0;
-      for (int q = 0; q < cnt; q++) {
-        const int i = forward ? (int)lo + q : (int)hi - 1 - q;
-        const int p = ipiv[i] - 1;
-        if (p == i) continue;
-        // locate slot of i (always in part a) and of p
-        const int ia = i - (int)lo;
-        int ip;  // slot index 0..63
-        if (p >= lo && p < hi) ip = p - (int)lo;
-        else {
-          unsigned hit = __ballot_sync(0xffffffffu, row_b == p);
-          if (hit) ip = 32 + (__ffs(hit) - 1);
-          else {
-            ip = 32 + nextra;
-            if (lane == nextra) { row_b = p; cur_b = p; }
-            nextra++;
-          }
-        }
-        // swap the contents of slots ia and ip
-        int ca = __shfl_sync(0xffffffffu, cur_a, ia);
-        int cp = (ip < 32) ? __shfl_sync(0xffffffffu, cur_a, ip) : __shfl_sync(0xffffffffu, cur_b, ip - 32);
-        if (lane == ia) cur_a = cp;
-        if (ip < 32) { if (lane == ip) cur_a = ca; }
-        else { if (lane == ip - 32) cur_b = ca; }
-      }
-      s_rows[lane] = (lane < cnt) ? row_a : -1;
-      s_src[lane] = (lane < cnt) ? cur_a : -1;
-      s_rows[32 + lane] = (lane < nextra) ? row_b : -1;
-      s_src[32 + lane] = (lane < nextra) ? cur_b : -1;
-      if (lane == 0) s_n = nextra;
-    }
+    if (tid < 32) laswp_compose_chunk(tid, lo, hi, forward, ipiv, s_rows, s_src);
     __syncthreads();
     const int dst = s_rows[s], src = s_src[s];
     const bool act = col_ok && dst >= 0 && dst != src;
@@ -375,10 +376,93 @@ __global__ void __launch_bounds__(2 * SW_CHUNK * SW_COLS) lla_dlaswp_kernel(doub
   }
 }
 
+// Long interchange sequences (a whole outer panel: up to 512 swaps) on many columns: the rows [k1, k2) of the
+// CTA's 16 columns are loaded into shared memory once (coalesced), all chunk permutations are composed up front
+// by eight warps in parallel, and the chunks are then applied one after the other with only the rows OUTSIDE
+// [k1, k2) touching global memory (a later chunk may revisit such a row: same CTA, ordered by the barriers).
+constexpr int LS_R = 512;
+constexpr int LS_CB = 16;
+constexpr int LS_T = 256;
+constexpr size_t LS_SMEM = (size_t)LS_R * LS_CB * sizeof(double);
+
+__global__ void __launch_bounds__(LS_T) lla_dlaswp_dense_kernel(double* __restrict__ A, int64_t lda, int64_t ncols,
+                                                                int64_t skip0, int64_t skip1, int64_t k1, int64_t k2,
+                                                                const int* __restrict__ ipiv, bool forward,
+                                                                const int* abort_flag) {
+  if (abort_flag != nullptr && *abort_flag != 0) return;
+  extern __shared__ __align__(16) double Dn[];
+  __shared__ int s_dst[LS_R / SW_CHUNK][2 * SW_CHUNK];
+  __shared__ int s_src[LS_R / SW_CHUNK][2 * SW_CHUNK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = (int)(k2 - k1);
+  const int nch = (R + SW_CHUNK - 1) / SW_CHUNK;
+  const int64_t skipw = skip1 - skip0;
+  const int64_t cbase = (int64_t)blockIdx.x * LS_CB;
+  auto column = [&](int cl) -> int64_t {  // global column of local column cl, or -1
+    int64_t c = cbase + cl;
+    if (c >= skip0) c += skipw;
+    return c < ncols ? c : -1;
+  };
+  for (int ch = warp; ch < nch; ch += LS_T / 32) {
+    int64_t lo, hi;
+    if (forward) { lo = k1 + (int64_t)ch * SW_CHUNK; hi = lo + SW_CHUNK < k2 ? lo + SW_CHUNK : k2; }
+    else { hi = k2 - (int64_t)ch * SW_CHUNK; lo = hi - SW_CHUNK > k1 ? hi - SW_CHUNK : k1; }
+    laswp_compose_chunk(lane, lo, hi, forward, ipiv, s_dst[ch], s_src[ch]);
+  }
+  for (int idx = tid; idx < R * LS_CB; idx += LS_T) {
+    const int r = idx % R, cl = idx / R;
+    const int64_t c = column(cl);
+    if (c >= 0) Dn[cl * LS_R + r] = A[k1 + r + c * lda];
+  }
+  __syncthreads();
+  const int s = tid % (2 * SW_CHUNK), cl0 = tid / (2 * SW_CHUNK);  // 4 column groups of 64 slots
+  for (int ch = 0; ch < nch; ch++) {
+    const int dst = s_dst[ch][s], src = s_src[ch][s];
+    const bool moves = dst >= 0 && dst != src;
+    double v[LS_CB / 4];
+#pragma unroll
+    for (int i = 0; i < LS_CB / 4; i++) {
+      const int cl = cl0 + 4 * i;
+      const int64_t c = column(cl);
+      v[i] = 0.0;
+      if (moves && c >= 0) v[i] = (src >= k1 && src < k2) ? Dn[cl * LS_R + (src - (int)k1)] : A[src + c * lda];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < LS_CB / 4; i++) {
+      const int cl = cl0 + 4 * i;
+      const int64_t c = column(cl);
+      if (moves && c >= 0) {
+        if (dst >= k1 && dst < k2) Dn[cl * LS_R + (dst - (int)k1)] = v[i];
+        else A[dst + c * lda] = v[i];
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < R * LS_CB; idx += LS_T) {
+    const int r = idx % R, cl = idx / R;
+    const int64_t c = column(cl);
+    if (c >= 0) A[k1 + r + c * lda] = Dn[cl * LS_R + r];
+  }
+}
+
 int dlaswp_skip_dev(int64_t ncols, int64_t skip0, int64_t skip1, double* A, int64_t lda, int64_t k1, int64_t k2,
                     const int* ipiv, bool forward, cudaStream_t st, const int* abort_flag) {
   int64_t eff = ncols - (skip1 - skip0);
   if (eff <= 0 || k2 <= k1) return 0;
+  static const bool no_dense = getenv("LLACUDA_LASWP_OLD") != nullptr;
+  if (k2 - k1 > 2 * SW_CHUNK && k2 - k1 <= LS_R && !no_dense) {
+    static bool configured = false;
+    if (!configured) {
+      LLA_CUDA(cudaFuncSetAttribute(lla_dlaswp_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
+      configured = true;
+    }
+    unsigned g = (unsigned)((eff + LS_CB - 1) / LS_CB);
+    lla_dlaswp_dense_kernel<<<g, LS_T, LS_SMEM, st>>>(A, lda, ncols, skip0, skip1, k1, k2, ipiv, forward, abort_flag);
+    count_launch();
+    LLA_CUDA(cudaGetLastError());
+    return 0;
+  }
   unsigned grid = (unsigned)((eff + SW_COLS - 1) / SW_COLS);
   lla_dlaswp_kernel<<<grid, 2 * SW_CHUNK * SW_COLS, 0, st>>>(A, lda, ncols, skip0, skip1, k1, k2, ipiv, forward, abort_flag);
   count_launch();
