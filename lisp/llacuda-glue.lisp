@@ -42,6 +42,8 @@
 
 (defparameter *llacuda-routines*
   '(("D" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs"))
+    ("S" . ("gemm"))
+    ("C" . ("gemm"))
     ("Z" . ("gemm")))
   "Routines libllacuda.so exports as llacuda_<letter><name> with the Fortran signature.")
 
