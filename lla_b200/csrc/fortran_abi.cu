@@ -71,35 +71,51 @@ static int dgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, double al
     tm.finish();
     return 0;
   }
+  // 2-D pipeline: op(A) = A is cut into RC row blocks, op(B) = B / C into `chunks` column blocks.  Uploads are queued
+  // as A_0, B_0 .. B_last, A_1 ..; block (r, c) of C is computed as soon as A_r and B_c (and C_rc when beta != 0)
+  // have arrived and goes back at once, so only A_0 + B_0 on the way in and the last block on the way out are
+  // exposed.  Each GEMM keeps >= ~7 waves of 128x64 tiles so that the per-launch tail stays around 1 %.
   cudaStream_t sh = cx->h2d, sd = cx->d2h;
-  cudaEvent_t ev_in[8], ev_done[8], ev_start;
+  const int RC = (!oa && m >= 8192) ? 2 : 1;
+  const int64_t rstep = RC == 1 ? m : ((m + RC - 1) / RC + 127) / 128 * 128;
+  const int64_t step = ((n + chunks - 1) / chunks + 63) / 64 * 64;
+  constexpr int MAXB = 2 * 8;
+  cudaEvent_t ev_in[MAXB], ev_done[MAXB], ev_start;
   LLA_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-  for (int j = 0; j < chunks; j++) {
+  for (int j = 0; j < RC * chunks; j++) {
     LLA_CUDA(cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming));
     LLA_CUDA(cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming));
   }
   LLA_CUDA(cudaEventRecord(ev_start, st));
   LLA_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
   LLA_CUDA(cudaStreamWaitEvent(sd, ev_start, 0));
-  LLA_TRY(stage_upload(sa, a, lda, sh));
-  const int64_t step = ((n + chunks - 1) / chunks + 63) / 64 * 64;
-  for (int j = 0; j < chunks; j++) {
-    const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
-    if (c0 >= n) { LLA_CUDA(cudaEventRecord(ev_in[j], sh)); continue; }
-    LLA_TRY(stage_upload_cols(sb, b, ldb, c0, c1, sh));
-    if (beta != 0.0) LLA_TRY(stage_upload_cols(sc, c, ldc, c0, c1, sh));
-    LLA_CUDA(cudaEventRecord(ev_in[j], sh));
+  for (int r = 0; r < RC; r++) {
+    const int64_t r0 = (int64_t)r * rstep, r1 = (r0 + rstep < m) ? r0 + rstep : m;
+    if (RC == 1) LLA_TRY(stage_upload(sa, a, lda, sh));
+    else LLA_TRY(stage_upload_block(sa, a, lda, r0, r1, 0, k, sh));
+    for (int j = 0; j < chunks; j++) {
+      const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
+      if (c0 < n) {
+        if (r == 0) LLA_TRY(stage_upload_cols(sb, b, ldb, c0, c1, sh));
+        if (beta != 0.0) LLA_TRY(stage_upload_block(sc, c, ldc, r0, r1, c0, c1, sh));
+      }
+      LLA_CUDA(cudaEventRecord(ev_in[r * chunks + j], sh));
+    }
   }
   tm.mark(1);
-  for (int j = 0; j < chunks; j++) {
-    const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
-    if (c0 >= n) break;
-    LLA_CUDA(cudaStreamWaitEvent(st, ev_in[j], 0));
-    LLA_TRY(dgemm_dev(oa, ob, m, c1 - c0, k, alpha, sa.ptr<double>(), sa.ld, sb.ptr<double>() + c0 * sb.ld, sb.ld, beta,
-                      sc.ptr<double>() + c0 * sc.ld, sc.ld, TRI_FULL, st));
-    LLA_CUDA(cudaEventRecord(ev_done[j], st));
-    LLA_CUDA(cudaStreamWaitEvent(sd, ev_done[j], 0));
-    LLA_TRY(stage_download_cols(sc, c, ldc, c0, c1, sd));
+  for (int r = 0; r < RC; r++) {
+    const int64_t r0 = (int64_t)r * rstep, r1 = (r0 + rstep < m) ? r0 + rstep : m;
+    if (r0 >= m) break;
+    for (int j = 0; j < chunks; j++) {
+      const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
+      if (c0 >= n) break;
+      LLA_CUDA(cudaStreamWaitEvent(st, ev_in[r * chunks + j], 0));
+      LLA_TRY(dgemm_dev(oa, ob, r1 - r0, c1 - c0, k, alpha, sa.ptr<double>() + r0, sa.ld, sb.ptr<double>() + c0 * sb.ld, sb.ld,
+                        beta, sc.ptr<double>() + r0 + c0 * sc.ld, sc.ld, TRI_FULL, st));
+      LLA_CUDA(cudaEventRecord(ev_done[r * chunks + j], st));
+      LLA_CUDA(cudaStreamWaitEvent(sd, ev_done[r * chunks + j], 0));
+      LLA_TRY(stage_download_block(sc, c, ldc, r0, r1, c0, c1, sd));
+    }
   }
   tm.mark(2);
   LLA_CUDA(cudaEventRecord(ev_start, sd));
@@ -109,7 +125,7 @@ static int dgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, double al
   LLA_CUDA(cudaStreamSynchronize(sd));
   tm.finish();
   cudaEventDestroy(ev_start);
-  for (int j = 0; j < chunks; j++) { cudaEventDestroy(ev_in[j]); cudaEventDestroy(ev_done[j]); }
+  for (int j = 0; j < RC * chunks; j++) { cudaEventDestroy(ev_in[j]); cudaEventDestroy(ev_done[j]); }
   return 0;
 }
 

@@ -99,6 +99,22 @@ int stage_download_cols(const Staged& s, void* host, int64_t ldh, int64_t c0, in
   return 0;
 }
 
+int stage_upload_block(Staged& s, const void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t st) {
+  if (r1 <= r0 || c1 <= c0) return 0;
+  LLA_CUDA(cudaMemcpy2DAsync((char*)s.buf.p + ((size_t)c0 * s.ld + r0) * s.es, (size_t)s.ld * s.es,
+                             (const char*)host + ((size_t)c0 * ldh + r0) * s.es, (size_t)ldh * s.es,
+                             (size_t)(r1 - r0) * s.es, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+int stage_download_block(const Staged& s, void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t st) {
+  if (r1 <= r0 || c1 <= c0) return 0;
+  LLA_CUDA(cudaMemcpy2DAsync((char*)host + ((size_t)c0 * ldh + r0) * s.es, (size_t)ldh * s.es,
+                             (const char*)s.buf.p + ((size_t)c0 * s.ld + r0) * s.es, (size_t)s.ld * s.es,
+                             (size_t)(r1 - r0) * s.es, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
 int stage_upload_tri(Staged& s, const void* host, int64_t ldh, bool upper, cudaStream_t st, int64_t chunk) {
   for (int64_t c0 = 0; c0 < s.cols; c0 += chunk) {
     const int64_t c1 = c0 + chunk < s.cols ? c0 + chunk : s.cols;

@@ -31,6 +31,9 @@ struct Staged {
 int stage_alloc(Staged& s, int64_t rows, int64_t cols, size_t es);
 int stage_upload(Staged& s, const void* host, int64_t ldh, cudaStream_t st);
 int stage_download(const Staged& s, void* host, int64_t ldh, cudaStream_t st);
+// rows [r0, r1) of the columns [c0, c1)
+int stage_upload_block(Staged& s, const void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t st);
+int stage_download_block(const Staged& s, void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t st);
 // only the named triangle (incl. diagonal) of a square matrix, as trapezoids of `chunk` columns
 int stage_upload_tri(Staged& s, const void* host, int64_t ldh, bool upper, cudaStream_t st, int64_t chunk = 512);
 int stage_download_tri(const Staged& s, void* host, int64_t ldh, bool upper, int64_t r0, cudaStream_t st, int64_t chunk = 512);

@@ -254,3 +254,20 @@ def test_cmm_types():
     got = L.mm(a, b)
     assert got.dtype == np.complex64
     assert np.allclose(got, a.astype(np.complex128) @ b.astype(np.float64), atol=1e-4)
+
+
+def test_dgemm_host_two_dimensional_pipeline():
+    """The host-pointer dgemm_ cuts big products into 2 row blocks x 8 column blocks that are uploaded, multiplied and
+    downloaded as a pipeline (csrc/fortran_abi.cu); Fortran m >= 8192 and 2 m n k > 4e10 select that path.  With
+    LLA's row-major convention (C^T = B^T A^T) Fortran's m is the row-major number of columns."""
+    rng = np.random.default_rng(21)
+    m, n, k = 2176, 8192, 1200
+    a = rng.uniform(-1, 1, (m, k))
+    b = rng.uniform(-1, 1, (k, n))
+    c = rng.uniform(-1, 1, (m, n))
+    want0 = a @ b
+    got = L.mm(a, b)
+    tol = gemm_tol(np.abs(a), np.abs(b), k)
+    assert np.all(np.abs(got - want0) <= tol)
+    got = L.gemm(0.7, a, b, 1.3, c.copy())
+    assert np.all(np.abs(got - (0.7 * want0 + 1.3 * c)) <= 0.7 * tol + 8 * EPS * 1.3 * np.abs(c))
