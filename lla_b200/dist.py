@@ -107,6 +107,12 @@ def device_gemm(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
     D.dgemm("N", "N", m, n, k, alpha, A.data_ptr(), lda, B.data_ptr(), ldb, beta, C.data_ptr(), ldc)
 
 
+def device_zgemm(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+    """Local complex-double C = alpha A B + beta C on the DMMA ZGEMM kernel (torch complex128 CUDA tensors)."""
+    from . import device as D
+    D.zgemm("N", "N", m, n, k, complex(alpha), A.data_ptr(), lda, B.data_ptr(), ldb, complex(beta), C.data_ptr(), ldc)
+
+
 def torch_gemm(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
     """CPU stand-in with the same signature (tests of the distribution logic only)."""
     a = A.reshape(-1)[: lda * k].view(k, lda)[:, :m].t()       # m x k
@@ -115,8 +121,8 @@ def torch_gemm(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
     c.copy_((alpha * (a @ b) + beta * c.t()).t())
 
 
-def summa(grid: Grid, m, n, k, nb, A_loc, B_loc, C_loc, local_gemm=device_gemm, lookahead=True):
-    """C = A B for block-cyclic operands (SUMMA).  *_loc are local column-major images:
+def summa(grid: Grid, m, n, k, nb, A_loc, B_loc, C_loc, local_gemm=None, lookahead=True):
+    """C = A B for block-cyclic operands (SUMMA), double or complex double (the local kernel follows the dtype).  *_loc are local column-major images:
     A_loc (k/Q, m/P), B_loc (n/Q, k/P), C_loc (n/Q, m/P).  One k-panel per step: the owning grid
     column broadcasts its slice of A along the grid rows, the owning grid row its slice of B along
     the grid columns (NCCL over NVLink); with `lookahead` the broadcasts of step s+1 are in flight
@@ -125,6 +131,8 @@ def summa(grid: Grid, m, n, k, nb, A_loc, B_loc, C_loc, local_gemm=device_gemm, 
     mloc, nloc = m // P, n // Q
     steps = k // nb
     dev, dt = C_loc.device, C_loc.dtype
+    if local_gemm is None:
+        local_gemm = device_zgemm if dt.is_complex else device_gemm
     abuf = [torch.empty((nb, mloc), dtype=dt, device=dev) for _ in range(2)]   # A panel: mloc x nb, ld = mloc
     bbuf = [torch.empty((nloc, nb), dtype=dt, device=dev) for _ in range(2)]   # B panel: nb x nloc, ld = nb
 

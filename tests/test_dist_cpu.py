@@ -29,6 +29,12 @@ for (P, Q) in ((1, 2), (2, 1)):
         C = lc.gather_to_global(C_loc)
         want = (A.t() @ B.t()).t()
         assert torch.allclose(C, want, atol=1e-12), (P, Q, look)
+    # complex double (configs[4] names ZGEMM): same schedule, panels broadcast as complex tensors
+    Az = torch.complex(torch.rand((k, m), dtype=torch.float64), torch.rand((k, m), dtype=torch.float64))
+    Bz = torch.complex(torch.rand((n, k), dtype=torch.float64), torch.rand((n, k), dtype=torch.float64))
+    Cz_loc = torch.zeros((n // Q, m // P), dtype=torch.complex128)
+    LD.summa(grid, m, n, k, nb, la.scatter_from_global(Az), lb.scatter_from_global(Bz), Cz_loc, local_gemm=LD.torch_gemm)
+    assert torch.allclose(lc.gather_to_global(Cz_loc), (Az.t() @ Bz.t()).t(), atol=1e-12), (P, Q, "complex")
 assert LD.choose_grid(8) == (2, 4) and LD.choose_grid(4) == (2, 2) and LD.choose_grid(2) == (1, 2)
 dist.destroy_process_group()
 """
