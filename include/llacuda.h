@@ -100,10 +100,6 @@ int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv
 int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, int* info_dev);
 int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const double* A, int64_t lda, double* B,
                        int64_t ldb);
-/* batched small solves (BASELINE configs[3]): `batch` independent n x n systems, n <= 32,
- * nrhs <= 8; system i lives at A + i*strideA (column-major, lda = n) and B + i*strideB (ldb = n).
- * X overwrites B; ipiv_dev (batch*n, may be NULL) and info_dev (batch) follow DGESV; A is only
- * overwritten with the LU factors when keep_lu != 0 (LLA's solve discards them). */
 /* op(T) X = B in place, T triangular m x m, B m x n (side = 'L', alpha = 1): LLA's trsm%
  * (reference src/linear-algebra.lisp:333-347); used by the block-cyclic factorisations. */
 int llacuda_dtrsm_dev(char uplo, char trans, char diag, int64_t m, int64_t n, const double* T, int64_t ldt,
@@ -111,6 +107,10 @@ int llacuda_dtrsm_dev(char uplo, char trans, char diag, int64_t m, int64_t n, co
 /* rows i <-> ipiv[i]-1 for i in [k1, k2) (0-based i, 1-based LAPACK pivots) on ncols columns, forward or reverse
  * order: the DLASWP step of GETRF/GETRS (reference call sites src/linear-algebra.lisp:227-234, 269-276). */
 int llacuda_dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv_dev, int forward);
+/* batched small solves (BASELINE configs[3]): `batch` independent n x n systems, n <= 32,
+ * nrhs <= 8; system i lives at A + i*strideA (column-major, lda = n) and B + i*strideB (ldb = n).
+ * X overwrites B; ipiv_dev (batch*n, may be NULL) and info_dev (batch) follow DGESV; A is only
+ * overwritten with the LU factors when keep_lu != 0 (LLA's solve discards them). */
 int llacuda_dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t strideA, int* ipiv_dev,
                               double* B, int64_t strideB, int* info_dev, int keep_lu);
 /* out[c + r*ldout] = in[r + c*ldin]: the device-side replacement of LLA's

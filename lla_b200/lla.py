@@ -238,6 +238,8 @@ class Cholesky:
 def solve(a, b):
     """reference src/linear-algebra.lisp:257-301, dispatching on the class of A like the generic function."""
     b = np.asarray(b)
+    if isinstance(a, (DeviceLU, DeviceCholesky)):
+        return _solve_device(a, b)
     if isinstance(a, LU):
         lu0, lu1 = a.lu.shape
         b0, b1, _ = dimensions_as_matrix(b, "column")
@@ -295,6 +297,150 @@ def cholesky(a) -> Cholesky:
     _fn(t, "potrf")(_chr("U"), _int(a0), _ptr(mem), _int(a0), ctypes.byref(info))
     _check_info(info.value)
     return Cholesky(np.tril(mem))
+
+
+# ------------------------------------------------------------------ device-resident factorization objects
+# the reference re-marshals the factors on every call -- `solve ((lu lu) b)` transposes the
+# stored n x n LU into foreign memory each time (src/linear-algebra.lisp:264-276, src/foreign-memory.lisp:211-255).
+# These objects keep the factors in HBM in LAPACK's column-major layout; the row-major <-> column-major conversion of
+# the operands runs on the device (llacuda_dtranspose_dev, HBM-bound) instead of the element-wise host loops, and a
+# solve moves only B and X over PCIe.  Double precision only (the device factorisations are D).
+class _DevBuf:
+    def __init__(self, nbytes):
+        self.p = ctypes.c_void_p()
+        self.nbytes = nbytes
+        _lib.check(_lib.lib().llacuda_malloc(ctypes.byref(self.p), ctypes.c_size_t(max(nbytes, 16))), "malloc")
+
+    def __del__(self):
+        try:
+            if self.p:
+                _lib.lib().llacuda_free(self.p)
+                self.p = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def _dev():
+    from . import device as D
+    _lib.lib().llacuda_reset_stream()      # the library's own stream: the blocking memcpy helpers synchronise on it
+    return D
+
+
+def _upload_colmajor(a):
+    """Row-major (a0, a1) float64 array -> device buffer holding the column-major a0 x a1 matrix (ld = a0)."""
+    D = _dev()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    a0, a1 = a.shape
+    raw, cm = _DevBuf(a.nbytes), _DevBuf(a.nbytes)
+    _lib.check(_lib.lib().llacuda_memcpy_h2d(raw.p, _ptr(a), ctypes.c_size_t(a.nbytes)), "h2d")
+    # the row-major bytes are the column-major image of a^T (a1 x a0, ld = a1): transpose it on the device
+    D.dtranspose(a1, a0, raw.p, a1, cm.p, a0)
+    return cm
+
+
+def _download_rowmajor(cm, a0, a1):
+    """Device column-major a0 x a1 matrix (ld = a0) -> row-major (a0, a1) numpy array."""
+    D = _dev()
+    raw = _DevBuf(a0 * a1 * 8)
+    D.dtranspose(a0, a1, cm.p, a0, raw.p, a1)
+    out = np.empty((a0, a1), dtype=np.float64)
+    _lib.check(_lib.lib().llacuda_memcpy_d2h(_ptr(out), raw.p, ctypes.c_size_t(out.nbytes)), "d2h")
+    return out
+
+
+class DeviceLU(LU):
+    """`lu` object whose factors and pivots live on the device; `.lu` / `.ipiv_internal` download on first use."""
+
+    def __init__(self, shape, d_lu, d_ipiv):
+        self.shape, self._d_lu, self._d_ipiv = shape, d_lu, d_ipiv
+        self._lu = self._ipiv = None
+
+    @property
+    def lu(self):
+        if self._lu is None:
+            self._lu = _download_rowmajor(self._d_lu, *self.shape)
+        return self._lu
+
+    @property
+    def ipiv_internal(self):
+        if self._ipiv is None:
+            k = min(self.shape)
+            self._ipiv = np.zeros(k, dtype=np.int32)
+            _lib.check(_lib.lib().llacuda_memcpy_d2h(_ptr(self._ipiv), self._d_ipiv.p, ctypes.c_size_t(4 * k)), "d2h")
+        return self._ipiv
+
+
+class DeviceCholesky(Cholesky):
+    """`cholesky` object whose factor lives on the device (POTRF 'U' of the untransposed row-major buffer = the
+    row-major lower factor, reference notes.org:32-37); `.left` downloads on first use."""
+
+    def __init__(self, n, d_u):
+        self.n, self._d_u = n, d_u
+        self._left = None
+
+    @property
+    def left(self):
+        if self._left is None:
+            out = np.empty((self.n, self.n), dtype=np.float64)
+            _lib.check(_lib.lib().llacuda_memcpy_d2h(_ptr(out), self._d_u.p, ctypes.c_size_t(out.nbytes)), "d2h")
+            self._left = np.tril(out)
+        return self._left
+
+
+def _device_info(d_info, condition):
+    info = ctypes.c_int(0)
+    _lib.check(_lib.lib().llacuda_memcpy_d2h(ctypes.byref(info), d_info.p, ctypes.c_size_t(4)), "d2h")
+    _check_info(info.value, condition)
+
+
+def lu_device(a) -> DeviceLU:
+    """`lu` (reference src/linear-algebra.lisp:225-234) keeping the result on the device."""
+    a = np.asarray(a)
+    if common_float_type(a) != DOUBLE:
+        raise NotImplementedError("device-resident factorisations are double precision only")
+    a0, a1 = a.shape
+    D = _dev()
+    d_lu = _upload_colmajor(a)
+    d_ipiv, d_info = _DevBuf(4 * max(min(a0, a1), 1)), _DevBuf(4)
+    D.dgetrf(a0, a1, d_lu.p, a0, d_ipiv.p, d_info.p)
+    _device_info(d_info, None)   # INFO > 0 is ignored by lu (src/linear-algebra.lisp:234)
+    return DeviceLU((a0, a1), d_lu, d_ipiv)
+
+
+def cholesky_device(a) -> DeviceCholesky:
+    """`cholesky` (reference src/linear-algebra.lisp:666-674) keeping the factor on the device."""
+    a = np.ascontiguousarray(a)
+    if common_float_type(a) != DOUBLE:
+        raise NotImplementedError("device-resident factorisations are double precision only")
+    a0, a1 = a.shape
+    if a0 != a1:
+        raise LlaIncompatibleDimensions()
+    D = _dev()
+    a = a.astype(np.float64, copy=False)
+    d_u, d_info = _DevBuf(a.nbytes), _DevBuf(4)
+    _lib.check(_lib.lib().llacuda_memcpy_h2d(d_u.p, _ptr(a), ctypes.c_size_t(a.nbytes)), "h2d")
+    D.dpotrf("U", a0, d_u.p, a0, d_info.p)
+    _device_info(d_info, LapackFailure)
+    return DeviceCholesky(a0, d_u)
+
+
+def _solve_device(f, b):
+    b = np.asarray(b)
+    b0, b1, vec = dimensions_as_matrix(b, "column")
+    n = f.shape[0] if isinstance(f, DeviceLU) else f.n
+    if isinstance(f, DeviceLU) and f.shape[0] != f.shape[1]:
+        raise LlaIncompatibleDimensions()
+    if n != b0:
+        raise LlaIncompatibleDimensions()
+    D = _dev()
+    d_b = _upload_colmajor(np.asarray(b, dtype=np.float64).reshape(b0, b1))
+    if isinstance(f, DeviceLU):
+        D.dgetrs("N", n, b1, f._d_lu.p, n, f._d_ipiv.p, d_b.p, n)
+    else:
+        D.dpotrs("U", n, b1, f._d_u.p, n, d_b.p, n)
+    x = _download_rowmajor(d_b, b0, b1)
+    _check_device_error()
+    return x.reshape(b.shape)
 
 
 # ------------------------------------------------------------------ factorization post-processing

@@ -304,3 +304,39 @@ def test_pinned_host_overlapped_downloads_match_pageable(n):
     u = np.triu(res[1].T)
     assert np.all(res[1][np.triu_indices(n, 1)] == -777.0), "the other triangle must come back untouched"
     assert np.linalg.norm(u.T @ u - spd) / (n * EPS * np.linalg.norm(spd)) <= 10
+
+
+# ------------------------------------------------------------------ device-resident factorisation objects
+@pytest.mark.parametrize("n", [7, 300, 1500])
+def test_device_resident_lu_and_cholesky_objects(n):
+    """lu_device / cholesky_device keep the factors in HBM (column-major, converted on the device); solves move only
+    B and X.  Same kernels on the same numbers as the host-pointer path, so factors and pivots are identical."""
+    rng = np.random.default_rng(n + 1)
+    a = rng.uniform(0, 10, (n, n))
+    b = rng.uniform(0, 10, (n, 3))
+    f, fd = L.lu(a), L.lu_device(a)
+    assert isinstance(fd, L.LU)
+    assert np.array_equal(fd.ipiv_internal, f.ipiv_internal)
+    assert np.array_equal(fd.lu, f.lu)
+    for rhs in (b, b[:, 0]):
+        x, xd = L.solve(f, rhs), L.solve(fd, rhs)
+        assert xd.shape == x.shape
+        assert np.allclose(xd, x, rtol=0, atol=1e-13 * np.abs(x).max())
+        assert residual(a, xd.reshape(n, -1), rhs.reshape(n, -1)) <= 10
+    assert np.array_equal(L.lu_u(fd), L.lu_u(f)) and np.array_equal(L.ipiv(fd.ipiv_internal), L.ipiv(f.ipiv_internal))
+    spd = a @ a.T + n * np.eye(n)
+    c, cd = L.cholesky(spd), L.cholesky_device(spd)
+    assert isinstance(cd, L.Cholesky)
+    assert np.array_equal(cd.left, c.left)
+    y, yd = L.solve(c, b), L.solve(cd, b)
+    assert np.allclose(yd, y, rtol=0, atol=1e-13 * np.abs(y).max())
+    with pytest.raises(L.LlaIncompatibleDimensions):
+        L.solve(fd, np.ones(n + 1))
+    bad = spd.copy(); bad[n // 2, n // 2] = -1.0
+    with pytest.raises(L.LapackFailure) as e:
+        L.cholesky_device(bad)
+    assert e.value.info == n // 2 + 1
+    # rectangular lu stays rectangular
+    r = rng.uniform(0, 10, (n, n + 5))
+    fr, frd = L.lu(r), L.lu_device(r)
+    assert np.array_equal(frd.ipiv_internal, fr.ipiv_internal) and np.array_equal(frd.lu, fr.lu)
