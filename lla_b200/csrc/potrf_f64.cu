@@ -94,19 +94,21 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
   const int64_t NB = NB_env > 0 ? NB_env : (n >= 12288 ? 1024 : 512);
   if (n <= 2 * NB) return potrf_rec(n, A, lda, 0, uinv, info, s1);
   cudaStream_t s2 = getenv("LLACUDA_NO_LOOKAHEAD") ? s1 : c->aux;
-  cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2];
+  cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2], ev_diag = c->ev[3];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
   LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+  bool rest_pending = false;  // part (a2) of the previous step: the block row right of the next diagonal block
   for (int64_t k = 0; k < n; k += NB) {
     const int64_t kb = (n - k) < NB ? (n - k) : NB;
     const int64_t n2 = n - k - kb;
     double* Akk = A + k + k * lda;
     double* Arow = Akk + kb * lda;             // block row right of the diagonal block
     double* uk = uinv + (k / IB) * IB * IB;
-    // ---- panel k on s2 (its inputs were produced by part (a) of the previous update)
+    // ---- panel k on s2: the diagonal block needs only part (a1) of the previous update, the block row also (a2)
     trace_mark(s2, "chol.panel>", k, kb);
     LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, s2));
     trace_mark(s2, "chol.trsm>", k, n2);
+    if (rest_pending) LLA_CUDA(cudaStreamWaitEvent(s2, ev_row, 0));
     if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, s2, info));
     trace_mark(s2, "chol.panel<", k, kb);
     LLA_CUDA(cudaEventRecord(ev_panel, s2));
@@ -116,12 +118,18 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
     const int64_t kb_next = n2 < NB ? n2 : NB;
     double* Anext = Arow + kb;                   // A[k+kb, k+kb]
-    // (a) block row of the next panel: rows [k+kb, k+kb+kb_next), columns [k+kb, n)
+    // (a1) the next diagonal block, (a2) the rest of the next panel's block row: rows [k+kb, k+kb+kb_next), columns [k+kb, n)
     trace_mark(s1, "chol.updA>", k, n2);
-    LLA_TRY(dgemm_dev(1, 0, kb_next, n2, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, s1, info));
+    LLA_TRY(dgemm_dev(1, 0, kb_next, kb_next, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, s1, info));
+    LLA_CUDA(cudaEventRecord(ev_diag, s1));
+    LLA_CUDA(cudaStreamWaitEvent(s2, ev_diag, 0));
+    rest_pending = n2 > kb_next;
+    if (rest_pending) {
+      LLA_TRY(dgemm_dev(1, 0, kb_next, n2 - kb_next, kb, -1.0, Arow, lda, Arow + kb_next * lda, lda, 1.0,
+                        Anext + kb_next * lda, lda, TRI_FULL, s1, info));
+      LLA_CUDA(cudaEventRecord(ev_row, s1));
+    }
     trace_mark(s1, "chol.updA<", k, n2);
-    LLA_CUDA(cudaEventRecord(ev_row, s1));
-    LLA_CUDA(cudaStreamWaitEvent(s2, ev_row, 0));
     // (b) the rest: rows [k+kb+kb_next, n)
     const int64_t n3 = n2 - kb_next;
     if (n3 > 0) {
