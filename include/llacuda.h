@@ -118,54 +118,62 @@ int llacuda_dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t
 int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out,
                            int64_t ldout);
 
+/* Integer type of the Fortran symbols: 32-bit, or 64-bit when the library is built with -DLLACUDA_ILP64
+ * (lla_b200/libllacuda64.so) for an LLA compiled with :int64 (reference src/types.lisp:7-8). */
+#ifdef LLACUDA_ILP64
+typedef int64_t llacuda_int;
+#else
+typedef int llacuda_int;
+#endif
+
 /* ------------------------------------------------------------------ Fortran drop-ins */
 /* reference call sites: mm  src/linear-algebra.lisp:50-54 ; gemm!  src/blas.lisp:56-63 */
-void dgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-            const double* alpha, const double* a, const int* lda, const double* b, const int* ldb,
-            const double* beta, double* c, const int* ldc);
-void llacuda_dgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                   const double* alpha, const double* a, const int* lda, const double* b,
-                   const int* ldb, const double* beta, double* c, const int* ldc);
+void dgemm_(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+            const double* alpha, const double* a, const llacuda_int* lda, const double* b, const llacuda_int* ldb,
+            const double* beta, double* c, const llacuda_int* ldc);
+void llacuda_dgemm(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+                   const double* alpha, const double* a, const llacuda_int* lda, const double* b,
+                   const llacuda_int* ldb, const double* beta, double* c, const llacuda_int* ldc);
 
-void sgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-            const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
-            const float* beta, float* c, const int* ldc);
-void llacuda_sgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                   const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
-                   const float* beta, float* c, const int* ldc);
-void cgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-            const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
-            const void* beta, void* c, const int* ldc);
-void llacuda_cgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                   const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
-                   const void* beta, void* c, const int* ldc);
-void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-            const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
-            const void* beta, void* c, const int* ldc);
-void llacuda_zgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                   const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
-                   const void* beta, void* c, const int* ldc);
+void sgemm_(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+            const float* alpha, const float* a, const llacuda_int* lda, const float* b, const llacuda_int* ldb,
+            const float* beta, float* c, const llacuda_int* ldc);
+void llacuda_sgemm(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+                   const float* alpha, const float* a, const llacuda_int* lda, const float* b, const llacuda_int* ldb,
+                   const float* beta, float* c, const llacuda_int* ldc);
+void cgemm_(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+            const void* alpha, const void* a, const llacuda_int* lda, const void* b, const llacuda_int* ldb,
+            const void* beta, void* c, const llacuda_int* ldc);
+void llacuda_cgemm(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+                   const void* alpha, const void* a, const llacuda_int* lda, const void* b, const llacuda_int* ldb,
+                   const void* beta, void* c, const llacuda_int* ldc);
+void zgemm_(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+            const void* alpha, const void* a, const llacuda_int* lda, const void* b, const llacuda_int* ldb,
+            const void* beta, void* c, const llacuda_int* ldc);
+void llacuda_zgemm(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+                   const void* alpha, const void* a, const llacuda_int* lda, const void* b, const llacuda_int* ldb,
+                   const void* beta, void* c, const llacuda_int* ldc);
 /* lu: src/linear-algebra.lisp:227-234 */
-void dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+void dgetrf_(const llacuda_int* m, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
 /* solve (lu): src/linear-algebra.lisp:269-276 */
-void dgetrs_(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda,
-             const int* ipiv, double* b, const int* ldb, int* info);
+void dgetrs_(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, double* b, const llacuda_int* ldb, llacuda_int* info);
 /* solve (array array): src/linear-algebra.lisp:282-289 */
-void dgesv_(const int* n, const int* nrhs, double* a, const int* lda, int* ipiv, double* b,
-            const int* ldb, int* info);
+void dgesv_(const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda, llacuda_int* ipiv, double* b,
+            const llacuda_int* ldb, llacuda_int* info);
 /* cholesky: src/linear-algebra.lisp:670-674 */
-void dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+void dpotrf_(const char* uplo, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* info);
 /* solve (cholesky): src/linear-algebra.lisp:296-301 */
-void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda,
-             double* b, const int* ldb, int* info);
-void llacuda_dgetrf(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
-void llacuda_dgetrs(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda,
-                    const int* ipiv, double* b, const int* ldb, int* info);
-void llacuda_dgesv(const int* n, const int* nrhs, double* a, const int* lda, int* ipiv, double* b,
-                   const int* ldb, int* info);
-void llacuda_dpotrf(const char* uplo, const int* n, double* a, const int* lda, int* info);
-void llacuda_dpotrs(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda,
-                    double* b, const int* ldb, int* info);
+void dpotrs_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda,
+             double* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_dgetrf(const llacuda_int* m, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void llacuda_dgetrs(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda,
+                    const llacuda_int* ipiv, double* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_dgesv(const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda, llacuda_int* ipiv, double* b,
+                   const llacuda_int* ldb, llacuda_int* info);
+void llacuda_dpotrf(const char* uplo, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_dpotrs(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda,
+                    double* b, const llacuda_int* ldb, llacuda_int* info);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libllacuda.so")
+SO64_PATH = os.path.join(_HERE, "libllacuda64.so")   # Fortran symbols with 64-bit integers (LLA compiled with :int64)
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None
@@ -21,7 +22,7 @@ class LlacudaError(RuntimeError):
 
 
 def build(force: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into lla_b200/libllacuda.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into lla_b200/libllacuda.so and libllacuda64.so (nvcc cross-compiles without a GPU)."""
     if force:
         subprocess.check_call(["make", "-C", CSRC, "clean", "-s"])
     subprocess.check_call(["make", "-C", CSRC, "-j", str(min(16, os.cpu_count() or 4)), "-s"])

@@ -152,6 +152,7 @@ using namespace llacuda;
 
 extern "C" int llacuda_dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t strideA, int* ipiv_dev,
                                          double* B, int64_t strideB, int* info_dev, int keep_lu) {
+  ApiLock api_lock;
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   if (strideA < (int64_t)n * n || strideB < (int64_t)n * (nrhs > 0 ? nrhs : 1)) return LLACUDA_ERR_BAD_ARG;

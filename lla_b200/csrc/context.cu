@@ -17,6 +17,9 @@
 namespace llacuda {
 
 static std::mutex g_mu;
+static std::recursive_mutex g_api_mu;
+ApiLock::ApiLock() { g_api_mu.lock(); }
+ApiLock::~ApiLock() { g_api_mu.unlock(); }
 static Context* g_ctx = nullptr;
 static thread_local char g_err[512] = "";
 static thread_local int g_err_code = 0;

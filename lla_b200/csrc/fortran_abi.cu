@@ -8,12 +8,14 @@
 #include "../../include/llacuda.h"
 
 #include <cstdio>
+#include <vector>
 
 using namespace llacuda;
 
 #define LLA_EXPORT extern "C"
 
 static int opcode(char c) {
+  ApiLock api_lock;
   switch (c) {
     case 'N': case 'n': return 0;
     case 'T': case 't': return 1;
@@ -129,9 +131,10 @@ static int dgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, double al
   return 0;
 }
 
-LLA_EXPORT void dgemm_(const char* transa, const char* transb, const int* m_, const int* n_, const int* k_,
-                       const double* alpha, const double* a, const int* lda_, const double* b, const int* ldb_,
-                       const double* beta, double* c, const int* ldc_) {
+LLA_EXPORT void dgemm_(const char* transa, const char* transb, const fint* m_, const fint* n_, const fint* k_,
+                       const double* alpha, const double* a, const fint* lda_, const double* b, const fint* ldb_,
+                       const double* beta, double* c, const fint* ldc_) {
+  ApiLock api_lock;
   int oa = opcode(*transa), ob = opcode(*transb);
   int64_t m = *m_, n = *n_, k = *k_, lda = *lda_, ldb = *ldb_, ldc = *ldc_;
   int64_t nrowa = oa ? k : m, nrowb = ob ? n : k;
@@ -149,14 +152,34 @@ LLA_EXPORT void dgemm_(const char* transa, const char* transb, const int* m_, co
   if (r != 0) fprintf(stderr, " ** llacuda: dgemm_ failed: %s\n", llacuda_last_error());
 }
 
-LLA_EXPORT void llacuda_dgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                              const double* alpha, const double* a, const int* lda, const double* b,
-                              const int* ldb, const double* beta, double* c, const int* ldc) {
+LLA_EXPORT void llacuda_dgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
+                              const double* alpha, const double* a, const fint* lda, const double* b,
+                              const fint* ldb, const double* beta, double* c, const fint* ldc) {
+  ApiLock api_lock;
   dgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }
 
 // ------------------------------------------------------------------ LAPACK drop-ins
 static inline int64_t max1(int64_t x) { return x > 1 ? x : 1; }
+
+// Integer vectors crossing the Fortran ABI: the device works on int32; with -DLLACUDA_ILP64 the caller's cells are
+// 64-bit and are converted through a 32-bit host vector (pivots are row indices < 2^31 for every matrix that fits).
+struct IntOut {
+  fint* dst; int64_t n; std::vector<int> tmp;
+  IntOut(fint* d, int64_t count) : dst(d), n(count) { if (sizeof(fint) != sizeof(int)) tmp.resize((size_t)(count > 0 ? count : 1)); }
+  int* host32() { return sizeof(fint) == sizeof(int) ? (int*)dst : tmp.data(); }
+  void finish() { if (sizeof(fint) != sizeof(int)) for (int64_t i = 0; i < n; i++) dst[i] = (fint)tmp[(size_t)i]; }
+};
+struct IntIn {
+  std::vector<int> tmp; const int* p;
+  IntIn(const fint* src, int64_t count) {
+    if (sizeof(fint) == sizeof(int)) { p = (const int*)src; return; }
+    tmp.resize((size_t)(count > 0 ? count : 1));
+    for (int64_t i = 0; i < count; i++) tmp[(size_t)i] = (int)src[i];
+    p = tmp.data();
+  }
+  const int* host32() const { return p; }
+};
 
 // Finished block rows of a factor go back to the caller while the factorisation is still running
 // (RowsFinalHook of the blocked drivers).  Only for page-locked host memory: a D2H copy into pageable
@@ -210,7 +233,7 @@ struct RowSender {
 
 // reads the device INFO word back; a CUDA failure overrides it with the out-of-band code
 
-static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, int* ipiv, int* info) {
+static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, fint* ipiv, fint* info) {
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   cudaStream_t st = cx->stream;
@@ -232,16 +255,19 @@ static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, int* ipiv, 
   tm.mark(2);
   LLA_TRY(stage_download_rows(sa, a, lda, rs.sent_upto, m, 0, st));
   LLA_CUDA(cudaStreamSynchronize(cx->d2h));
-  if (mn > 0) LLA_CUDA(cudaMemcpyAsync(ipiv, piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
-  LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  IntOut pivots(ipiv, mn), inf_out(info, 1);
+  if (mn > 0) LLA_CUDA(cudaMemcpyAsync(pivots.host32(), piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
+  LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   LLA_CUDA(cudaStreamSynchronize(st));
+  pivots.finish(); inf_out.finish();
   tm.finish();
   return 0;
 }
 
 /* reference call site: lu, src/linear-algebra.lisp:227-234 */
-LLA_EXPORT void dgetrf_(const int* m_, const int* n_, double* a, const int* lda_, int* ipiv, int* info) {
+LLA_EXPORT void dgetrf_(const fint* m_, const fint* n_, double* a, const fint* lda_, fint* ipiv, fint* info) {
+  ApiLock api_lock;
   int64_t m = *m_, n = *n_, lda = *lda_;
   *info = 0;
   if (m < 0) { *info = -1; return; }
@@ -252,7 +278,7 @@ LLA_EXPORT void dgetrf_(const int* m_, const int* n_, double* a, const int* lda_
   if (rc != 0) *info = rc;
 }
 
-static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t lda, const int* ipiv, double* b,
+static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t lda, const fint* ipiv, double* b,
                        int64_t ldb) {
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
@@ -266,7 +292,8 @@ static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t
   LLA_TRY(piv.alloc(sizeof(int) * (size_t)n));
   LLA_TRY(stage_upload(sa, a, lda, st));
   LLA_TRY(stage_upload(sb, b, ldb, st));
-  LLA_CUDA(cudaMemcpyAsync(piv.p, ipiv, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+  IntIn pivots(ipiv, n);
+  LLA_CUDA(cudaMemcpyAsync(piv.p, pivots.host32(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
   tm.mark(1);
   LLA_TRY(dgetrs_dev(op, n, nrhs, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st));
   tm.mark(2);
@@ -278,8 +305,9 @@ static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t
 }
 
 /* reference call site: solve (lu), src/linear-algebra.lisp:269-276 */
-LLA_EXPORT void dgetrs_(const char* trans, const int* n_, const int* nrhs_, const double* a, const int* lda_,
-                        const int* ipiv, double* b, const int* ldb_, int* info) {
+LLA_EXPORT void dgetrs_(const char* trans, const fint* n_, const fint* nrhs_, const double* a, const fint* lda_,
+                        const fint* ipiv, double* b, const fint* ldb_, fint* info) {
+  ApiLock api_lock;
   int op = opcode(*trans);
   int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
   *info = 0;
@@ -293,8 +321,8 @@ LLA_EXPORT void dgetrs_(const char* trans, const int* n_, const int* nrhs_, cons
   if (rc != 0) *info = rc;
 }
 
-static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, int* ipiv, double* b, int64_t ldb,
-                      int* info) {
+static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ipiv, double* b, int64_t ldb,
+                      fint* info) {
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   cudaStream_t st = cx->stream;
@@ -321,17 +349,20 @@ static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, int* ipiv
   LLA_TRY(stage_download_rows(sa, a, lda, rs.sent_upto, n, 0, st));
   LLA_CUDA(cudaStreamSynchronize(cx->d2h));
   LLA_TRY(stage_download(sb, b, ldb, st));
-  LLA_CUDA(cudaMemcpyAsync(ipiv, piv.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  IntOut pivots(ipiv, n), inf_out(info, 1);
+  LLA_CUDA(cudaMemcpyAsync(pivots.host32(), piv.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   LLA_CUDA(cudaStreamSynchronize(st));
+  pivots.finish(); inf_out.finish();
   tm.finish();
   return 0;
 }
 
 /* reference call site: solve (array array), src/linear-algebra.lisp:282-289 */
-LLA_EXPORT void dgesv_(const int* n_, const int* nrhs_, double* a, const int* lda_, int* ipiv, double* b,
-                       const int* ldb_, int* info) {
+LLA_EXPORT void dgesv_(const fint* n_, const fint* nrhs_, double* a, const fint* lda_, fint* ipiv, double* b,
+                       const fint* ldb_, fint* info) {
+  ApiLock api_lock;
   int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
   *info = 0;
   if (n < 0) { *info = -1; return; }
@@ -343,7 +374,7 @@ LLA_EXPORT void dgesv_(const int* n_, const int* nrhs_, double* a, const int* ld
   if (rc != 0) *info = rc;
 }
 
-static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, int* info) {
+static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, fint* info) {
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   cudaStream_t st = cx->stream;
@@ -365,15 +396,18 @@ static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, int* info)
   tm.mark(2);
   LLA_TRY(stage_download_tri(sa, a, lda, upper, rs.sent_upto, st));
   LLA_CUDA(cudaStreamSynchronize(cx->d2h));
-  LLA_CUDA(cudaMemcpyAsync(info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  IntOut inf_out(info, 1);
+  LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   LLA_CUDA(cudaStreamSynchronize(st));
+  inf_out.finish();
   tm.finish();
   return 0;
 }
 
 /* reference call site: cholesky, src/linear-algebra.lisp:670-674 (always UPLO = 'U') */
-LLA_EXPORT void dpotrf_(const char* uplo, const int* n_, double* a, const int* lda_, int* info) {
+LLA_EXPORT void dpotrf_(const char* uplo, const fint* n_, double* a, const fint* lda_, fint* info) {
+  ApiLock api_lock;
   int64_t n = *n_, lda = *lda_;
   bool upper = (*uplo == 'U' || *uplo == 'u');
   bool lower = (*uplo == 'L' || *uplo == 'l');
@@ -408,8 +442,9 @@ static int dpotrs_host(bool upper, int64_t n, int64_t nrhs, const double* a, int
 }
 
 /* reference call site: solve (cholesky), src/linear-algebra.lisp:296-301 */
-LLA_EXPORT void dpotrs_(const char* uplo, const int* n_, const int* nrhs_, const double* a, const int* lda_,
-                        double* b, const int* ldb_, int* info) {
+LLA_EXPORT void dpotrs_(const char* uplo, const fint* n_, const fint* nrhs_, const double* a, const fint* lda_,
+                        double* b, const fint* ldb_, fint* info) {
+  ApiLock api_lock;
   int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
   bool upper = (*uplo == 'U' || *uplo == 'u');
   bool lower = (*uplo == 'L' || *uplo == 'l');
@@ -425,27 +460,33 @@ LLA_EXPORT void dpotrs_(const char* uplo, const int* n_, const int* nrhs_, const
 }
 
 // llacuda_<name> aliases (INTEGRATION.md option B: re-pointed blas-lapack-function-name)
-LLA_EXPORT void llacuda_dgetrf(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info) {
+LLA_EXPORT void llacuda_dgetrf(const fint* m, const fint* n, double* a, const fint* lda, fint* ipiv, fint* info) {
+  ApiLock api_lock;
   dgetrf_(m, n, a, lda, ipiv, info);
 }
-LLA_EXPORT void llacuda_dgetrs(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda,
-                               const int* ipiv, double* b, const int* ldb, int* info) {
+LLA_EXPORT void llacuda_dgetrs(const char* trans, const fint* n, const fint* nrhs, const double* a, const fint* lda,
+                               const fint* ipiv, double* b, const fint* ldb, fint* info) {
+  ApiLock api_lock;
   dgetrs_(trans, n, nrhs, a, lda, ipiv, b, ldb, info);
 }
-LLA_EXPORT void llacuda_dgesv(const int* n, const int* nrhs, double* a, const int* lda, int* ipiv, double* b,
-                              const int* ldb, int* info) {
+LLA_EXPORT void llacuda_dgesv(const fint* n, const fint* nrhs, double* a, const fint* lda, fint* ipiv, double* b,
+                              const fint* ldb, fint* info) {
+  ApiLock api_lock;
   dgesv_(n, nrhs, a, lda, ipiv, b, ldb, info);
 }
-LLA_EXPORT void llacuda_dpotrf(const char* uplo, const int* n, double* a, const int* lda, int* info) {
+LLA_EXPORT void llacuda_dpotrf(const char* uplo, const fint* n, double* a, const fint* lda, fint* info) {
+  ApiLock api_lock;
   dpotrf_(uplo, n, a, lda, info);
 }
-LLA_EXPORT void llacuda_dpotrs(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda,
-                               double* b, const int* ldb, int* info) {
+LLA_EXPORT void llacuda_dpotrs(const char* uplo, const fint* n, const fint* nrhs, const double* a, const fint* lda,
+                               double* b, const fint* ldb, fint* info) {
+  ApiLock api_lock;
   dpotrs_(uplo, n, nrhs, a, lda, b, ldb, info);
 }
 
 // ------------------------------------------------------------------ device-pointer API
 LLA_EXPORT int llacuda_dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv_dev, int* info_dev) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   if (m < 0 || n < 0 || lda < max1(m)) return LLACUDA_ERR_BAD_ARG;
@@ -453,6 +494,7 @@ LLA_EXPORT int llacuda_dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, 
 }
 LLA_EXPORT int llacuda_dgetrs_dev(char trans, int64_t n, int64_t nrhs, const double* A, int64_t lda,
                                   const int* ipiv_dev, double* B, int64_t ldb) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   int op = opcode(trans);
@@ -461,6 +503,7 @@ LLA_EXPORT int llacuda_dgetrs_dev(char trans, int64_t n, int64_t nrhs, const dou
 }
 LLA_EXPORT int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv_dev, double* B,
                                  int64_t ldb, int* info_dev) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   if (n < 0 || nrhs < 0 || lda < max1(n) || ldb < max1(n)) return LLACUDA_ERR_BAD_ARG;
@@ -468,6 +511,7 @@ LLA_EXPORT int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda
   return dgetrs_dev(0, n, nrhs, A, lda, ipiv_dev, B, ldb, cx->stream, info_dev);
 }
 LLA_EXPORT int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, int* info_dev) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   bool upper = (uplo == 'U' || uplo == 'u');
@@ -476,6 +520,7 @@ LLA_EXPORT int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, 
 }
 LLA_EXPORT int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const double* A, int64_t lda, double* B,
                                   int64_t ldb) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   bool upper = (uplo == 'U' || uplo == 'u');
@@ -485,6 +530,7 @@ LLA_EXPORT int llacuda_dpotrs_dev(char uplo, int64_t n, int64_t nrhs, const doub
 }
 LLA_EXPORT int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out,
                                       int64_t ldout) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   return dtranspose_dev(rows, cols, in, ldin, out, ldout, cx->stream);
@@ -525,9 +571,10 @@ static int zgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuDoubleC
 }
 
 /* reference call sites: mm src/linear-algebra.lisp:50-54, gemm! src/blas.lisp:56-63 (complex-double arrays) */
-LLA_EXPORT void zgemm_(const char* transa, const char* transb, const int* m_, const int* n_, const int* k_,
-                       const void* alpha, const void* a, const int* lda_, const void* b, const int* ldb_,
-                       const void* beta, void* c, const int* ldc_) {
+LLA_EXPORT void zgemm_(const char* transa, const char* transb, const fint* m_, const fint* n_, const fint* k_,
+                       const void* alpha, const void* a, const fint* lda_, const void* b, const fint* ldb_,
+                       const void* beta, void* c, const fint* ldc_) {
+  ApiLock api_lock;
   int oa = opcode(*transa), ob = opcode(*transb);
   int64_t m = *m_, n = *n_, k = *k_, lda = *lda_, ldb = *ldb_, ldc = *ldc_;
   int64_t nrowa = oa ? k : m, nrowb = ob ? n : k;
@@ -545,14 +592,16 @@ LLA_EXPORT void zgemm_(const char* transa, const char* transb, const int* m_, co
                      (const cuDoubleComplex*)b, ldb, *(const cuDoubleComplex*)beta, (cuDoubleComplex*)c, ldc);
   if (r != 0) fprintf(stderr, " ** llacuda: zgemm_ failed: %s\n", llacuda_last_error());
 }
-LLA_EXPORT void llacuda_zgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                              const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
-                              const void* beta, void* c, const int* ldc) {
+LLA_EXPORT void llacuda_zgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
+                              const void* alpha, const void* a, const fint* lda, const void* b, const fint* ldb,
+                              const void* beta, void* c, const fint* ldc) {
+  ApiLock api_lock;
   zgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }
 LLA_EXPORT int llacuda_zgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const double* alpha2,
                                  const void* A, int64_t lda, const void* B, int64_t ldb, const double* beta2,
                                  void* C, int64_t ldc) {
+  ApiLock api_lock;
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   int oa = opcode(opa), ob = opcode(opb);
@@ -594,9 +643,10 @@ static int sgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, float alp
 }
 
 /* reference call sites: mm src/linear-algebra.lisp:50-54, gemm! src/blas.lisp:56-63 (single-float arrays) */
-LLA_EXPORT void sgemm_(const char* transa, const char* transb, const int* m_, const int* n_, const int* k_,
-                       const float* alpha, const float* a, const int* lda_, const float* b, const int* ldb_,
-                       const float* beta, float* c, const int* ldc_) {
+LLA_EXPORT void sgemm_(const char* transa, const char* transb, const fint* m_, const fint* n_, const fint* k_,
+                       const float* alpha, const float* a, const fint* lda_, const float* b, const fint* ldb_,
+                       const float* beta, float* c, const fint* ldc_) {
+  ApiLock api_lock;
   int oa = opcode(*transa), ob = opcode(*transb);
   int64_t m = *m_, n = *n_, k = *k_, lda = *lda_, ldb = *ldb_, ldc = *ldc_;
   int64_t nrowa = oa ? k : m, nrowb = ob ? n : k;
@@ -613,8 +663,9 @@ LLA_EXPORT void sgemm_(const char* transa, const char* transb, const int* m_, co
   int r = sgemm_host(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc);
   if (r != 0) fprintf(stderr, " ** llacuda: sgemm_ failed: %s\n", llacuda_last_error());
 }
-LLA_EXPORT void llacuda_sgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                              const float* alpha, const float* a, const int* lda, const float* b, const int* ldb,
-                              const float* beta, float* c, const int* ldc) {
+LLA_EXPORT void llacuda_sgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
+                              const float* alpha, const float* a, const fint* lda, const float* b, const fint* ldb,
+                              const float* beta, float* c, const fint* ldc) {
+  ApiLock api_lock;
   sgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }

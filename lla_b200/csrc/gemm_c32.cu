@@ -102,6 +102,7 @@ static int c_opcode(char c) {
 
 extern "C" int llacuda_cgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, const float* alpha2, const void* A,
                                  int64_t lda, const void* B, int64_t ldb, const float* beta2, void* C, int64_t ldc) {
+  ApiLock api_lock;
   int oa = c_opcode(opa), ob = c_opcode(opb);
   if (oa < 0 || ob < 0 || m < 0 || n < 0 || k < 0) return LLACUDA_ERR_BAD_ARG;
   Context* c = ctx();
@@ -142,9 +143,10 @@ static int cgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuFloatCo
 }
 
 /* reference call sites: mm src/linear-algebra.lisp:50-54, gemm! src/blas.lisp:56-63 (complex-single arrays) */
-extern "C" void cgemm_(const char* transa, const char* transb, const int* m_, const int* n_, const int* k_, const void* alpha,
-                       const void* a, const int* lda_, const void* b, const int* ldb_, const void* beta, void* c,
-                       const int* ldc_) {
+extern "C" void cgemm_(const char* transa, const char* transb, const fint* m_, const fint* n_, const fint* k_, const void* alpha,
+                       const void* a, const fint* lda_, const void* b, const fint* ldb_, const void* beta, void* c,
+                       const fint* ldc_) {
+  ApiLock api_lock;
   int oa = c_opcode(*transa), ob = c_opcode(*transb);
   int64_t m = *m_, n = *n_, k = *k_, lda = *lda_, ldb = *ldb_, ldc = *ldc_;
   int64_t nrowa = oa ? k : m, nrowb = ob ? n : k;
@@ -169,8 +171,9 @@ extern "C" void cgemm_(const char* transa, const char* transb, const int* m_, co
   if (r != 0) fprintf(stderr, " ** llacuda: cgemm_ failed: %s\n", llacuda_last_error());
 }
 
-extern "C" void llacuda_cgemm(const char* transa, const char* transb, const int* m, const int* n, const int* k,
-                              const void* alpha, const void* a, const int* lda, const void* b, const int* ldb,
-                              const void* beta, void* c, const int* ldc) {
+extern "C" void llacuda_cgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
+                              const void* alpha, const void* a, const fint* lda, const void* b, const fint* ldb,
+                              const void* beta, void* c, const fint* ldc) {
+  ApiLock api_lock;
   cgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }

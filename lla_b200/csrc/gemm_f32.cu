@@ -355,6 +355,7 @@ static int sopcode(char c) {
 
 extern "C" int llacuda_sgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, float alpha, const float* A,
                                  int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc) {
+  ApiLock api_lock;
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   int oa = sopcode(opa), ob = sopcode(opb);

@@ -364,6 +364,7 @@ static int opcode(char c) {
 extern "C" int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, double alpha,
                                       const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
                                       double* C, int64_t ldc, int tri) {
+  ApiLock api_lock;
   int oa = opcode(opa), ob = opcode(opb);
   if (oa < 0 || ob < 0 || m < 0 || n < 0 || k < 0 || tri < 0 || tri > 2) return LLACUDA_ERR_BAD_ARG;
   Context* c = ctx();
@@ -374,5 +375,6 @@ extern "C" int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, 
 extern "C" int llacuda_dgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, double alpha,
                                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
                                  double* C, int64_t ldc) {
+  ApiLock api_lock;
   return llacuda_dsyrk_like_dev(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0);
 }

@@ -6,6 +6,14 @@
 #include <stdint.h>
 #include <stddef.h>
 
+// Integer type of the Fortran-symbol layer: LLA passes 32-bit integers unless it was compiled with :int64
+// (reference src/types.lisp:7-8, src/foreign-memory.lisp:35-40); -DLLACUDA_ILP64 builds libllacuda64.so for that mode.
+#ifdef LLACUDA_ILP64
+typedef int64_t fint;
+#else
+typedef int fint;
+#endif
+
 namespace llacuda {
 
 // ------------------------------------------------------------------ errors
@@ -25,6 +33,14 @@ int  record_cuda_error(cudaError_t e, const char* file, int line);
     int _r = (call);                      \
     if (_r != 0) return _r;               \
   } while (0)
+
+// One process-global context and per-call arena: calls entering through the C ABI are serialised (LLA itself is
+// single-threaded, but user Lisp threads may call concurrently: SURVEY.md section 8b "Threading / reentrancy").
+// Recursive: the llacuda_<name> aliases call the Fortran symbols.
+struct ApiLock {
+  ApiLock();
+  ~ApiLock();
+};
 
 // ------------------------------------------------------------------ context
 struct Context {

@@ -711,6 +711,7 @@ using namespace llacuda;
 // processes of the block-cyclic LU (lla_b200/dist.py) apply to their own columns after a panel's pivots arrive.
 extern "C" int llacuda_dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv_dev,
                                   int forward) {
+  ApiLock api_lock;
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   if (ncols < 0 || k1 < 0 || k2 < k1 || lda < 1) return LLACUDA_ERR_BAD_ARG;

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) lla_dfma_probe_kernel(double* out, int it
 using namespace llacuda;
 
 extern "C" int llacuda_probe_fp64_peak(int kind, int iters, double* tflops, float* ms_out) {
+  ApiLock api_lock;
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   constexpr int CH = 16;

@@ -198,6 +198,7 @@ using namespace llacuda;
 // block-cyclic Cholesky / LU of lla_b200/dist.py runs on the block row that the diagonal owner broadcast.
 extern "C" int llacuda_dtrsm_dev(char uplo, char trans, char diag, int64_t m, int64_t n, const double* T, int64_t ldt,
                                  double* B, int64_t ldb) {
+  ApiLock api_lock;
   const bool upper = (uplo == 'U' || uplo == 'u'), lower = (uplo == 'L' || uplo == 'l');
   const bool unit = (diag == 'U' || diag == 'u'), nonunit = (diag == 'N' || diag == 'n');
   int op = -1;

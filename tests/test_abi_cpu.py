@@ -38,6 +38,26 @@ def test_fortran_symbol_set(lib):
         assert hasattr(lib, f"llacuda_d{routine}"), routine
 
 
+def test_ilp64_variant_exports_the_same_fortran_symbols(lib):
+    """libllacuda64.so: the same symbols with 64-bit integer cells (LLA :int64, reference src/types.lisp:7-8)."""
+    assert os.path.exists(_lib.SO64_PATH)
+    lib64 = ctypes.CDLL(_lib.SO64_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib64, s)]
+    assert not missing, missing
+    import torch
+    if torch.cuda.is_available():
+        return
+    # argument checking happens before any device work and uses the 64-bit cells: n = -1 in an int64 cell
+    import numpy as np
+    a = np.eye(4)
+    ipiv = np.zeros(4, dtype=np.int64)
+    info = ctypes.c_int64(7)
+    four, minus = ctypes.c_int64(4), ctypes.c_int64(-1)
+    lib64.dgetrf_(ctypes.byref(four), ctypes.byref(minus), a.ctypes.data_as(ctypes.c_void_p), ctypes.byref(four),
+                  ipiv.ctypes.data_as(ctypes.c_void_p), ctypes.byref(info))
+    assert info.value == -2
+
+
 def test_no_silent_cpu_fallback(lib):
     """Without a CUDA device the library must fail loudly, never compute on the host."""
     import torch

@@ -340,3 +340,31 @@ def test_device_resident_lu_and_cholesky_objects(n):
     r = rng.uniform(0, 10, (n, n + 5))
     fr, frd = L.lu(r), L.lu_device(r)
     assert np.array_equal(frd.ipiv_internal, fr.ipiv_internal) and np.array_equal(frd.lu, fr.lu)
+
+
+def test_ilp64_library_matches_lp64():
+    """libllacuda64.so (64-bit integer cells, LLA :int64): same factors, pivots and solution as libllacuda.so."""
+    import ctypes
+    from lla_b200 import _lib
+    lib32, lib64 = _lib.lib(), ctypes.CDLL(_lib.SO64_PATH)
+    n, nrhs = 700, 3
+    rng = np.random.default_rng(64)
+    a = np.asfortranarray(rng.uniform(0, 10, (n, n)))
+    b = np.asfortranarray(rng.uniform(0, 10, (n, nrhs)))
+    P = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    outs = []
+    for lib, ct, dt in ((lib32, ctypes.c_int, np.int32), (lib64, ctypes.c_int64, np.int64)):
+        aw, bw = np.ascontiguousarray(a.T), np.ascontiguousarray(b.T)      # column-major images
+        ipiv = np.zeros(n, dtype=dt); info = ct(0)
+        I = lambda v: ctypes.byref(ct(v))
+        lib.dgesv_(I(n), I(nrhs), P(aw), I(n), P(ipiv), P(bw), I(n), ctypes.byref(info))
+        assert info.value == 0
+        spd = np.ascontiguousarray((a @ a.T + n * np.eye(n)).T)
+        lib.dpotrf_(ctypes.c_char_p(b"U"), I(n), P(spd), I(n), ctypes.byref(info))
+        assert info.value == 0
+        bad = ct(0)
+        lib.dpotrf_(ctypes.c_char_p(b"U"), I(-3), P(spd), I(n), ctypes.byref(bad))
+        assert bad.value == -2
+        outs.append((aw, bw, ipiv.astype(np.int64), spd))
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y)
