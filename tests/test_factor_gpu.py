@@ -354,7 +354,7 @@ def test_ilp64_library_matches_lp64():
     P = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
     outs = []
     for lib, ct, dt in ((lib32, ctypes.c_int, np.int32), (lib64, ctypes.c_int64, np.int64)):
-        aw, bw = np.ascontiguousarray(a.T), np.ascontiguousarray(b.T)      # column-major images
+        aw, bw = a.T.copy(order="C"), b.T.copy(order="C")                  # column-major images (copies: a.T of an F-ordered array is already C-contiguous)
         ipiv = np.zeros(n, dtype=dt); info = ct(0)
         I = lambda v: ctypes.byref(ct(v))
         lib.dgesv_(I(n), I(nrhs), P(aw), I(n), P(ipiv), P(bw), I(n), ctypes.byref(info))
