@@ -175,6 +175,23 @@ void llacuda_dpotrf(const char* uplo, const llacuda_int* n, double* a, const lla
 void llacuda_dpotrs(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda,
                     double* b, const llacuda_int* ldb, llacuda_int* info);
 
+/* "next" rows: mm-hermitian% src/linear-algebra.lisp:62-76, solve on a hermitian-matrix
+ * :303-315, trsm% :333-347 */
+void dsyrk_(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const double* alpha,
+            const double* a, const llacuda_int* lda, const double* beta, double* c, const llacuda_int* ldc);
+void llacuda_dsyrk(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const double* alpha,
+                   const double* a, const llacuda_int* lda, const double* beta, double* c, const llacuda_int* ldc);
+void dtrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const llacuda_int* m,
+            const llacuda_int* n, const double* alpha, const double* a, const llacuda_int* lda, double* b,
+            const llacuda_int* ldb);
+void llacuda_dtrsm(const char* side, const char* uplo, const char* transa, const char* diag, const llacuda_int* m,
+                   const llacuda_int* n, const double* alpha, const double* a, const llacuda_int* lda, double* b,
+                   const llacuda_int* ldb);
+void dposv_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda, double* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_dposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda,
+                   double* b, const llacuda_int* ldb, llacuda_int* info);
+
 #ifdef __cplusplus
 }
 #endif

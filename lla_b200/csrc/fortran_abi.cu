@@ -536,6 +536,184 @@ LLA_EXPORT int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* 
   return dtranspose_dev(rows, cols, in, ldin, out, ldout, cx->stream);
 }
 
+// ------------------------------------------------------------------ "next" rows: SYRK, POSV, TRSM
+// C <- alpha A A^T + beta C ('N') or alpha A^T A + beta C ('T' / 'C'), only the uplo triangle of C referenced: the DMMA
+// GEMM restricted to that triangle.  The triangle travels as the 512-column trapezoids of stage_upload_tri in both
+// directions (uploaded even when beta = 0, so that the bytes of the other triangle inside the diagonal chunks come
+// back as they were).
+static int dsyrk_host(bool upper, int trans, int64_t n, int64_t k, double alpha, const double* a, int64_t lda, double beta,
+                      double* c, int64_t ldc) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  if (n == 0) return 0;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa, sc;
+  const bool need_a = k > 0 && alpha != 0.0;
+  if (need_a) {
+    LLA_TRY(stage_alloc(sa, trans ? k : n, trans ? n : k, sizeof(double)));
+    LLA_TRY(stage_upload(sa, a, lda, st));
+  }
+  LLA_TRY(stage_alloc(sc, n, n, sizeof(double)));
+  LLA_TRY(stage_upload_tri(sc, c, ldc, upper, st));
+  tm.mark(1);
+  LLA_TRY(dgemm_dev(trans ? 1 : 0, trans ? 0 : 1, n, n, need_a ? k : 0, alpha, sa.ptr<double>(), sa.ld, sa.ptr<double>(), sa.ld,
+                    beta, sc.ptr<double>(), sc.ld, upper ? TRI_UPPER : TRI_LOWER, st));
+  tm.mark(2);
+  LLA_TRY(stage_download_tri(sc, c, ldc, upper, 0, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: mm-hermitian%, src/linear-algebra.lisp:62-76 ((mm a t), (mm t a)) */
+LLA_EXPORT void dsyrk_(const char* uplo, const char* trans, const fint* n_, const fint* k_, const double* alpha,
+                       const double* a, const fint* lda_, const double* beta, double* c, const fint* ldc_) {
+  ApiLock api_lock;
+  const bool upper = (*uplo == 'U' || *uplo == 'u'), lower = (*uplo == 'L' || *uplo == 'l');
+  const int op = opcode(*trans);
+  const int64_t n = *n_, k = *k_, lda = *lda_, ldc = *ldc_;
+  const int64_t nrowa = op ? k : n;
+  int bad = 0;
+  if (!upper && !lower) bad = 1;
+  else if (op < 0) bad = 2;
+  else if (n < 0) bad = 3;
+  else if (k < 0) bad = 4;
+  else if (lda < (nrowa > 1 ? nrowa : 1)) bad = 7;
+  else if (ldc < (n > 1 ? n : 1)) bad = 10;
+  if (bad) { blas_arg_error("DSYRK ", bad); return; }
+  int r = dsyrk_host(upper, op, n, k, *alpha, a, lda, *beta, c, ldc);
+  if (r != 0) fprintf(stderr, " ** llacuda: dsyrk_ failed: %s\n", llacuda_last_error());
+}
+
+LLA_EXPORT void llacuda_dsyrk(const char* uplo, const char* trans, const fint* n, const fint* k, const double* alpha,
+                              const double* a, const fint* lda, const double* beta, double* c, const fint* ldc) {
+  dsyrk_(uplo, trans, n, k, alpha, a, lda, beta, c, ldc);
+}
+
+// op(A) X = alpha B (side 'L') or X op(A) = alpha B (side 'R'), A triangular.  The device solver is left-sided
+// (block inverses + DMMA GEMMs); a right-sided solve runs on the transposed right-hand side with op flipped.
+static int dtrsm_host(bool left, bool upper, int op, bool unit, int64_t m, int64_t n, double alpha, const double* a,
+                      int64_t lda, double* b, int64_t ldb) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  if (m == 0 || n == 0) return 0;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  const int64_t na = left ? m : n;
+  Staged sa, sb;
+  LLA_TRY(stage_alloc(sa, na, na, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, m, n, sizeof(double)));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  LLA_TRY(stage_upload(sb, b, ldb, st));
+  tm.mark(1);
+  if (alpha != 1.0)  // B <- alpha B (the k = 0 path of the GEMM driver)
+    LLA_TRY(dgemm_dev(0, 0, m, n, 0, 0.0, nullptr, 1, nullptr, 1, alpha, sb.ptr<double>(), sb.ld, TRI_FULL, st));
+  Arena ar;
+  LLA_TRY(ar.reserve(tinv_bytes(na) + 1024));
+  double* tinv = (double*)ar.take(tinv_bytes(na));
+  LLA_TRY(dtrtri_blocks_dev(upper, unit, na, sa.ptr<double>(), sa.ld, tinv, st));
+  if (left) {
+    LLA_TRY(dtrsm_left_inv_dev(upper, op ? 1 : 0, m, n, sa.ptr<double>(), sa.ld, tinv, sb.ptr<double>(), sb.ld, st));
+  } else {
+    Staged st_t;
+    LLA_TRY(stage_alloc(st_t, n, m, sizeof(double)));
+    LLA_TRY(dtranspose_dev(m, n, sb.ptr<double>(), sb.ld, st_t.ptr<double>(), st_t.ld, st));
+    LLA_TRY(dtrsm_left_inv_dev(upper, op ? 0 : 1, n, m, sa.ptr<double>(), sa.ld, tinv, st_t.ptr<double>(), st_t.ld, st));
+    LLA_TRY(dtranspose_dev(n, m, st_t.ptr<double>(), st_t.ld, sb.ptr<double>(), sb.ld, st));
+    LLA_CUDA(cudaStreamSynchronize(st));   // st_t goes back to the pool at the end of this scope
+  }
+  tm.mark(2);
+  LLA_TRY(stage_download(sb, b, ldb, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: trsm%, src/linear-algebra.lisp:333-347 (solve on triangular matrices): side 'R', 'N', 'N' */
+LLA_EXPORT void dtrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const fint* m_,
+                       const fint* n_, const double* alpha, const double* a, const fint* lda_, double* b, const fint* ldb_) {
+  ApiLock api_lock;
+  const bool left = (*side == 'L' || *side == 'l'), right = (*side == 'R' || *side == 'r');
+  const bool upper = (*uplo == 'U' || *uplo == 'u'), lower = (*uplo == 'L' || *uplo == 'l');
+  const bool unit = (*diag == 'U' || *diag == 'u'), nonunit = (*diag == 'N' || *diag == 'n');
+  const int op = opcode(*transa);
+  const int64_t m = *m_, n = *n_, lda = *lda_, ldb = *ldb_;
+  const int64_t nrowa = left ? m : n;
+  int bad = 0;
+  if (!left && !right) bad = 1;
+  else if (!upper && !lower) bad = 2;
+  else if (op < 0) bad = 3;
+  else if (!unit && !nonunit) bad = 4;
+  else if (m < 0) bad = 5;
+  else if (n < 0) bad = 6;
+  else if (lda < (nrowa > 1 ? nrowa : 1)) bad = 9;
+  else if (ldb < (m > 1 ? m : 1)) bad = 11;
+  if (bad) { blas_arg_error("DTRSM ", bad); return; }
+  int r = dtrsm_host(left, upper, op, unit, m, n, *alpha, a, lda, b, ldb);
+  if (r != 0) fprintf(stderr, " ** llacuda: dtrsm_ failed: %s\n", llacuda_last_error());
+}
+
+LLA_EXPORT void llacuda_dtrsm(const char* side, const char* uplo, const char* transa, const char* diag, const fint* m,
+                              const fint* n, const double* alpha, const double* a, const fint* lda, double* b, const fint* ldb) {
+  dtrsm_(side, uplo, transa, diag, m, n, alpha, a, lda, b, ldb);
+}
+
+// DPOSV = DPOTRF + DPOTRS, the solve gated by the device INFO word (no host round trip in between)
+static int dposv_host(bool upper, int64_t n, int64_t nrhs, double* a, int64_t lda, double* b, int64_t ldb, fint* info) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  PhaseTimer tm(st);
+  tm.mark(0);
+  Staged sa, sb;
+  PoolBuf inf;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
+  LLA_TRY(inf.alloc(sizeof(int)));
+  LLA_TRY(stage_upload_tri(sa, a, lda, upper, st));
+  LLA_TRY(stage_upload(sb, b, ldb, st));
+  tm.mark(1);
+  LLA_TRY(dpotrf_dev(upper, n, sa.ptr<double>(), sa.ld, (int*)inf.p, st));
+  LLA_TRY(dpotrs_dev(upper, n, nrhs, sa.ptr<double>(), sa.ld, sb.ptr<double>(), sb.ld, st, (const int*)inf.p));
+  tm.mark(2);
+  LLA_TRY(stage_download_tri(sa, a, lda, upper, 0, st));
+  LLA_TRY(stage_download(sb, b, ldb, st));
+  IntOut inf_out(info, 1);
+  LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
+  LLA_CUDA(cudaStreamSynchronize(st));
+  inf_out.finish();
+  tm.finish();
+  return 0;
+}
+
+/* reference call site: solve (hermitian-matrix), src/linear-algebra.lisp:303-315 */
+LLA_EXPORT void dposv_(const char* uplo, const fint* n_, const fint* nrhs_, double* a, const fint* lda_, double* b,
+                       const fint* ldb_, fint* info) {
+  ApiLock api_lock;
+  const bool upper = (*uplo == 'U' || *uplo == 'u'), lower = (*uplo == 'L' || *uplo == 'l');
+  const int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  *info = 0;
+  if (!upper && !lower) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (nrhs < 0) { *info = -3; return; }
+  if (lda < max1(n)) { *info = -5; return; }
+  if (ldb < max1(n)) { *info = -7; return; }
+  if (n == 0 || nrhs == 0) { if (n == 0) return; }
+  int rc = dposv_host(upper, n, nrhs, a, lda, b, ldb, info);
+  if (rc != 0) *info = rc;
+}
+
+LLA_EXPORT void llacuda_dposv(const char* uplo, const fint* n, const fint* nrhs, double* a, const fint* lda, double* b,
+                              const fint* ldb, fint* info) {
+  dposv_(uplo, n, nrhs, a, lda, b, ldb, info);
+}
+
 // ------------------------------------------------------------------ ZGEMM
 static int zgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
                       const cuDoubleComplex* a, int64_t lda, const cuDoubleComplex* b, int64_t ldb,

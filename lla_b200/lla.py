@@ -155,7 +155,11 @@ def _check_info(info, condition=LapackFailure):
 
 # ------------------------------------------------------------------ mm / gemm!
 def mm(a, b):
-    """reference src/linear-algebra.lisp:39-54."""
+    """reference src/linear-algebra.lisp:39-54; (mm a t) / (mm t a) are the hermitian products of :62-84."""
+    if b is True:
+        return mm_hermitian(a, False)
+    if a is True:
+        return mm_hermitian(b, True)
     a, b = np.asarray(a), np.asarray(b)
     t = common_float_type(a, b)
     a0, a1, av = dimensions_as_matrix(a, "row")
@@ -237,6 +241,12 @@ class Cholesky:
 
 def solve(a, b):
     """reference src/linear-algebra.lisp:257-301, dispatching on the class of A like the generic function."""
+    if isinstance(a, Hermitian):
+        return solve_hermitian(a, b)
+    if isinstance(a, LowerTriangular):
+        return trsm(a.elements, False, b)
+    if isinstance(a, UpperTriangular):
+        return trsm(a.elements, True, b)
     b = np.asarray(b)
     if isinstance(a, (DeviceLU, DeviceCholesky)):
         return _solve_device(a, b)
@@ -297,6 +307,78 @@ def cholesky(a) -> Cholesky:
     _fn(t, "potrf")(_chr("U"), _int(a0), _ptr(mem), _int(a0), ctypes.byref(info))
     _check_info(info.value)
     return Cholesky(np.tril(mem))
+
+
+# ------------------------------------------------------------------ "next" rows: mm-hermitian%, posv, trsm%
+class Hermitian:
+    """cl-num-utils hermitian-matrix: the row-major LOWER triangle of `elements` defines the matrix."""
+
+    def __init__(self, elements):
+        self.elements = np.asarray(elements)
+
+    def as_array(self):
+        low = np.tril(self.elements)
+        return low + np.tril(self.elements, -1).conj().T
+
+
+class LowerTriangular:
+    def __init__(self, elements):
+        self.elements = np.asarray(elements)
+
+
+class UpperTriangular:
+    def __init__(self, elements):
+        self.elements = np.asarray(elements)
+
+
+def mm_hermitian(a, transpose_left: bool) -> Hermitian:
+    """reference src/linear-algebra.lisp:62-76: (mm a t) = A A^T, (mm t a) = A^T A through SYRK('U') on the untransposed
+    row-major buffer (its column-major view is A^T, hence 'C' for A A^T and 'N' for A^T A)."""
+    a = np.asarray(a)
+    a0, a1 = a.shape
+    dim_c, other = (a1, a0) if transpose_left else (a0, a1)
+    t = common_float_type(a)
+    am = _as_memory(a, t)
+    c = np.zeros((dim_c, dim_c), dtype=_DTYPES[t])
+    (_k1, pone), (_k0, pzero) = _atom(1, t), _atom(0, t)
+    _fn(t, "syrk")(_chr("U"), _chr("N" if transpose_left else "C"), _int(dim_c), _int(other), pone, _ptr(am),
+                   _int(a1), pzero, _ptr(c), _int(dim_c))
+    _check_device_error()
+    return Hermitian(c)
+
+
+def solve_hermitian(a: Hermitian, b):
+    """reference src/linear-algebra.lisp:303-315: POSV('U') on a forced copy of the elements, B transposed in and out."""
+    el, b = a.elements, np.asarray(b)
+    a0, a1 = el.shape
+    b0, b1, _ = dimensions_as_matrix(b, "column")
+    if not (a0 == a1 == b0):
+        raise LlaIncompatibleDimensions()
+    t = common_float_type(el, b)
+    amem = np.array(el, dtype=_DTYPES[t], order="C", copy=True)
+    bmem = _transposed_to_memory(b, t)
+    info = ctypes.c_int(0)
+    _fn(t, "posv")(_chr("U"), _int(a0), _int(b1), _ptr(amem), _int(a0), _ptr(bmem), _int(b0), ctypes.byref(info))
+    _check_info(info.value)
+    return _transposed_from_memory(bmem, b.shape)
+
+
+def trsm(a, a_upper: bool, b):
+    """reference src/linear-algebra.lisp:333-347 (trsm%): A X = B for triangular A as TRSM('R', L/U swapped, 'N', 'N')
+    on the untransposed row-major buffers."""
+    a, b = np.asarray(a), np.asarray(b)
+    a0, a1 = a.shape
+    b0, b1, _ = dimensions_as_matrix(b, "column")
+    if not (a0 == a1 == b0):
+        raise LlaIncompatibleDimensions()
+    t = common_float_type(a, b)
+    am = _as_memory(a, t)
+    x = np.array(b, dtype=_DTYPES[t], order="C", copy=True).reshape(b0, b1)
+    _k1, pone = _atom(1, t)
+    _fn(t, "trsm")(_chr("R"), _chr("L" if a_upper else "U"), _chr("N"), _chr("N"), _int(b1), _int(b0), pone,
+                   _ptr(am), _int(a1), _ptr(x), _int(b1))
+    _check_device_error()
+    return x.reshape(b.shape)
 
 
 # ------------------------------------------------------------------ device-resident factorization objects

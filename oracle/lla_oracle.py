@@ -347,6 +347,59 @@ def solve_cholesky(c: Cholesky, b, be: Backend):
     return transpose_matrix_from_memory(bmem, b.shape)
 
 
+# ------------------------------------------------ "next" rows
+def mm_hermitian(a, transpose_left: bool, be: Backend):
+    """src/linear-algebra.lisp:62-76: (mm a t) = A A^T, (mm t a) = A^T A through SYRK('U') on the untransposed
+    row-major buffer (its column-major view is A^T, hence the swapped N / C); the result is wrapped as a
+    hermitian-matrix, which reads the row-major lower triangle = the column-major upper one SYRK wrote."""
+    a = np.asarray(a)
+    a0, a1 = a.shape
+    dim_c, other = (a1, a0) if transpose_left else (a0, a1)
+    t = common_float_type(a)
+    assert t in (SINGLE, DOUBLE), "complex arrays go through herk (out of scope)"
+    amem = copy_array_to_memory(a, t)
+    c = np.zeros((dim_c, dim_c), dtype=_DTYPES[t])
+    (_k1, one), (_k0, zero) = _atom(1, t), _atom(0, t)
+    be.fn(t, "syrk")(_chr("U"), _chr("N" if transpose_left else "C"), _int(dim_c), _int(other), one,
+                     _ptr(amem), _int(a1), zero, _ptr(c), _int(dim_c))
+    low = np.tril(c)
+    return low + np.tril(c, -1).T          # hermitian-matrix: the lower triangle defines the matrix
+
+
+def solve_hermitian(a, b, be: Backend):
+    """src/linear-algebra.lisp:303-315: POSV('U') on a forced copy of the row-major elements (only the row-major
+    lower triangle is read), B transposed in and out."""
+    a, b = np.asarray(a), np.asarray(b)
+    a0, a1 = a.shape
+    b0, b1, _ = dimensions_as_matrix(b, "column")
+    if not (a0 == a1 == b0):
+        raise LlaIncompatibleDimensions()
+    t = common_float_type(a, b)
+    amem = copy_array_to_memory(a, t)
+    bmem = transpose_matrix_to_memory(b, t)
+    info = ctypes.c_int(0)
+    be.fn(t, "posv")(_chr("U"), _int(a0), _int(b1), _ptr(amem), _int(a0), _ptr(bmem), _int(b0), ctypes.byref(info))
+    _check_info(info.value)
+    return transpose_matrix_from_memory(bmem, b.shape)
+
+
+def trsm(a, a_upper: bool, b, be: Backend):
+    """src/linear-algebra.lisp:333-347 (trsm%): solve A X = B for triangular A with TRSM('R', L/U swapped, 'N', 'N')
+    on the untransposed row-major buffers (X^T A^T = B^T in the column-major view)."""
+    a, b = np.asarray(a), np.asarray(b)
+    a0, a1 = a.shape
+    b0, b1, _ = dimensions_as_matrix(b, "column")
+    if not (a0 == a1 == b0):
+        raise LlaIncompatibleDimensions()
+    t = common_float_type(a, b)
+    amem = copy_array_to_memory(a, t)
+    xmem = copy_array_to_memory(b, t).reshape(b0, b1)
+    _k1, one = _atom(1, t)
+    be.fn(t, "trsm")(_chr("R"), _chr("L" if a_upper else "U"), _chr("N"), _chr("N"), _int(b1), _int(b0), one,
+                     _ptr(amem), _int(a1), _ptr(xmem), _int(b1))
+    return xmem.reshape(b.shape)
+
+
 # ------------------------------------------------ factorization post-processing
 def ipiv(ipiv_internal) -> np.ndarray:
     """src/factorizations.lisp:15-28: swap sequence -> 0-based permutation."""

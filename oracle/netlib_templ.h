@@ -259,6 +259,88 @@ void PFX(potrs_)(const char *uplo, const int *n_, const int *nrhs_, const T *a, 
   }
 }
 
+
+/* ------------------------------------------------------------------ "next" rows of SURVEY section 8f
+ * xSYRK  <- mm-hermitian%  src/linear-algebra.lisp:62-76   (real types; LLA sends herk for complex)
+ * xTRSM  <- trsm%          src/linear-algebra.lisp:333-347
+ * xPOSV  <- solve (hermitian-matrix)  src/linear-algebra.lisp:303-315  (= xPOTRF + xPOTRS)
+ * Reference BLAS loop orders (netlib dsyrk.f / dtrsm.f). */
+
+/* C <- alpha A A^T + beta C (trans = 'N', A n x k) or alpha A^T A + beta C (trans = 'T'/'C', A k x n); only the
+ * uplo triangle of C is referenced. */
+void PFX(syrk_)(const char *uplo, const char *trans, const int *n_, const int *k_, const T *alpha_, const T *a,
+                const int *lda_, const T *beta_, T *c, const int *ldc_) {
+  int64_t n = *n_, k = *k_, lda = *lda_, ldc = *ldc_;
+  T alpha = *alpha_, beta = *beta_;
+  int upper = PFX(lsame)(*uplo, 'U'), notr = PFX(lsame)(*trans, 'N');
+  for (int64_t j = 0; j < n; j++) {
+    int64_t i0 = upper ? 0 : j, i1 = upper ? j + 1 : n;
+    for (int64_t i = i0; i < i1; i++) {
+      T s = 0;
+      if (notr) { for (int64_t l = 0; l < k; l++) s += a[i + l * lda] * a[j + l * lda]; }
+      else { for (int64_t l = 0; l < k; l++) s += a[l + i * lda] * a[l + j * lda]; }
+      c[i + j * ldc] = (beta == (T)0) ? alpha * s : alpha * s + beta * c[i + j * ldc];
+    }
+  }
+}
+
+/* op(A) X = alpha B (side 'L') or X op(A) = alpha B (side 'R'); B (m x n) is overwritten by X. */
+void PFX(trsm_)(const char *side, const char *uplo, const char *transa, const char *diag, const int *m_, const int *n_,
+                const T *alpha_, const T *a, const int *lda_, T *b, const int *ldb_) {
+  int64_t m = *m_, n = *n_, lda = *lda_, ldb = *ldb_;
+  T alpha = *alpha_;
+  int left = PFX(lsame)(*side, 'L'), upper = PFX(lsame)(*uplo, 'U');
+  int tr = PFX(lsame)(*transa, 'N') ? 0 : (PFX(lsame)(*transa, 'T') ? 1 : 2);
+  int nounit = PFX(lsame)(*diag, 'N');
+  int64_t na = left ? m : n;
+  /* E = op(A) as an explicit na x na triangle accessor */
+#define OPA(i, j) (tr == 0 ? a[(i) + (j) * lda] : (tr == 1 ? a[(j) + (i) * lda] : CONJ(a[(j) + (i) * lda])))
+  int eff_upper = (tr == 0) ? upper : !upper;
+  for (int64_t j = 0; j < n; j++)
+    for (int64_t i = 0; i < m; i++) b[i + j * ldb] *= alpha;
+  if (left) {
+    for (int64_t j = 0; j < n; j++) {
+      if (eff_upper) {
+        for (int64_t i = m - 1; i >= 0; i--) {
+          T s = b[i + j * ldb];
+          for (int64_t l = i + 1; l < m; l++) s -= OPA(i, l) * b[l + j * ldb];
+          b[i + j * ldb] = nounit ? s / OPA(i, i) : s;
+        }
+      } else {
+        for (int64_t i = 0; i < m; i++) {
+          T s = b[i + j * ldb];
+          for (int64_t l = 0; l < i; l++) s -= OPA(i, l) * b[l + j * ldb];
+          b[i + j * ldb] = nounit ? s / OPA(i, i) : s;
+        }
+      }
+    }
+  } else {
+    /* X E = B  <=>  for each row i of X: E^T x = b */
+    for (int64_t i = 0; i < m; i++) {
+      if (eff_upper) {   /* E upper: x_j = (b_j - sum_{l<j} x_l E(l,j)) / E(j,j) */
+        for (int64_t j = 0; j < n; j++) {
+          T s = b[i + j * ldb];
+          for (int64_t l = 0; l < j; l++) s -= b[i + l * ldb] * OPA(l, j);
+          b[i + j * ldb] = nounit ? s / OPA(j, j) : s;
+        }
+      } else {
+        for (int64_t j = n - 1; j >= 0; j--) {
+          T s = b[i + j * ldb];
+          for (int64_t l = j + 1; l < n; l++) s -= b[i + l * ldb] * OPA(l, j);
+          b[i + j * ldb] = nounit ? s / OPA(j, j) : s;
+        }
+      }
+    }
+  }
+  (void)na;
+#undef OPA
+}
+
+void PFX(posv_)(const char *uplo, const int *n_, const int *nrhs_, T *a, const int *lda_, T *b, const int *ldb_, int *info) {
+  PFX(potrf_)(uplo, n_, a, lda_, info);
+  if (*info == 0) PFX(potrs_)(uplo, n_, nrhs_, a, lda_, b, ldb_, info);
+}
+
 #undef ABS1
 #undef CONJ
 #undef REAL

@@ -368,3 +368,42 @@ def test_ilp64_library_matches_lp64():
         outs.append((aw, bw, ipiv.astype(np.int64), spd))
     for x, y in zip(outs[0], outs[1]):
         assert np.array_equal(x, y)
+
+
+# ------------------------------------------------------------------ "next" rows on the device: dsyrk_, dtrsm_, dposv_
+def test_mm_hermitian_trsm_posv_reference_goldens():
+    a = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert np.array_equal(L.mm(a, True).as_array(), a @ a.T)          # tests/linear-algebra.lisp:117-124
+    assert np.array_equal(L.mm(True, a).as_array(), a.T @ a)
+    u, l, b = np.array([[1.0, 2.0], [0.0, 3.0]]), np.array([[1.0, 0.0], [2.0, 3.0]]), np.array([[5.0, 6.0], [7.0, 8.0]])
+    assert num_eq(u @ L.solve(L.UpperTriangular(u), b), b)              # :167-181
+    assert num_eq(l @ L.solve(L.LowerTriangular(l), b), b)
+    spd = np.array([[2.0, -1, 0], [-1, 2, -1], [0, -1, 2]])
+    rhs = np.array([5.0, 7.0, 13.0])
+    assert num_eq(L.solve(L.Hermitian(spd), rhs), L.solve(spd, rhs))    # :366-385
+    with pytest.raises(L.LapackFailure):
+        L.solve(L.Hermitian(-spd), rhs)
+
+
+@pytest.mark.parametrize("m,k", [(33, 7), (300, 129), (1100, 600)])
+def test_mm_hermitian_trsm_posv_vs_oracle(m, k):
+    rng = np.random.default_rng(m + k)
+    r = rng.uniform(-1, 1, (m, k))
+    for tl in (False, True):
+        got = L.mm_hermitian(r, tl)
+        want = O.mm_hermitian(r, tl, O.openblas())
+        kk = m if tl else k
+        tol = 4 * np.sqrt(kk) * EPS * (np.linalg.norm(r, axis=0 if tl else 1).max() ** 2)
+        assert np.max(np.abs(got.as_array() - want)) <= tol
+        assert np.all(np.triu(got.elements, 1) == 0.0), "SYRK('U') of the column-major view must not write the other triangle"
+    t = np.triu(rng.uniform(-1, 1, (m, m))) + 4 * np.eye(m)
+    b = rng.uniform(-1, 1, (m, 5))
+    for mat, upper in ((t, True), (t.T.copy(), False)):
+        x = L.trsm(mat, upper, b)
+        assert residual(mat, x, b) <= 10
+        xo = O.trsm(mat, upper, b, O.openblas())
+        assert np.max(np.abs(x - xo)) <= 1e-10 * np.abs(xo).max()
+    g = rng.uniform(0, 1, (m, m))
+    spd = g @ g.T + m * np.eye(m)
+    x = L.solve(L.Hermitian(spd), b)
+    assert residual(spd, x, b) <= 10

@@ -181,3 +181,34 @@ def test_ipiv_bit_exact_midsize():
     rng = np.random.default_rng(3)
     a = rng.uniform(0, 10, (300, 300))
     assert np.array_equal(O.lu(a, O.netlib()).ipiv_internal, O.lu(a, O.openblas()).ipiv_internal)
+
+
+# ------------------------------------------------------------------ "next" rows: mm-hermitian%, trsm%, posv
+@pytest.mark.parametrize("be", ["netlib", "openblas"])
+def test_next_rows_reference_goldens(be):
+    """tests/linear-algebra.lisp:117-124 (mm-hermitian), :167-181 (mm-solve-triangular), :366-385 ((solve a b) on the
+    hermitian matrix of the cholesky test)."""
+    be = getattr(O, be)()
+    a = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert np.array_equal(O.mm_hermitian(a, False, be), a @ a.T)
+    assert np.array_equal(O.mm_hermitian(a, True, be), a.T @ a)
+    u, l, b = np.array([[1.0, 2.0], [0.0, 3.0]]), np.array([[1.0, 0.0], [2.0, 3.0]]), np.array([[5.0, 6.0], [7.0, 8.0]])
+    assert np.allclose(u @ O.trsm(u, True, b, be), b, atol=1e-14)
+    assert np.allclose(l @ O.trsm(l, False, b, be), b, atol=1e-14)
+    spd = np.array([[2.0, -1, 0], [-1, 2, -1], [0, -1, 2]])
+    rhs = np.array([5.0, 7.0, 13.0])
+    assert np.allclose(O.solve_hermitian(spd, rhs, be), np.linalg.solve(spd, rhs), atol=1e-13)
+    # only the row-major lower triangle of a hermitian-matrix is read
+    junk = spd.copy(); junk[np.triu_indices(3, 1)] = 99.0
+    assert np.allclose(O.solve_hermitian(junk, rhs, be), np.linalg.solve(spd, rhs), atol=1e-13)
+
+
+def test_next_rows_backends_agree():
+    rng = np.random.default_rng(31)
+    r = rng.uniform(-1, 1, (40, 23))
+    for tl in (False, True):
+        assert np.allclose(O.mm_hermitian(r, tl, O.netlib()), O.mm_hermitian(r, tl, O.openblas()), atol=1e-13)
+    t = np.triu(rng.uniform(1, 2, (30, 30)))
+    b = rng.uniform(-1, 1, (30, 4))
+    assert np.allclose(O.trsm(t, True, b, O.netlib()), O.trsm(t, True, b, O.openblas()), rtol=1e-10)
+    assert np.allclose(O.trsm(t.T.copy(), False, b, O.netlib()), O.trsm(t.T.copy(), False, b, O.openblas()), rtol=1e-10)
