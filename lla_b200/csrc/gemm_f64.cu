@@ -300,14 +300,17 @@ static int launch_shape(const DgemmParams& p, cudaStream_t st, int sm_count, int
   if (p.tri != TRI_FULL) big_tiles = big_tiles / 2 + 1;
   if (big_tiles >= 2 * (int64_t)sm_count) {
     // measured on B200 (profiles/r01_gemm_config_sweep.txt): two 128x64 CTAs per SM hide each
-    // other's barrier bubbles (33.6 vs 31.5 TFLOP/s) unless op(A) is K-contiguous, where the
-    // 128x128 tile with BK = 32 is the faster one (32.2 vs 25.9 TFLOP/s).
+    // other's barrier bubbles (33.6 vs 31.5 TFLOP/s for one 128x128 CTA).
     static int cfg = -1;
     if (cfg < 0) { const char* e = getenv("LLACUDA_GEMM_CFG"); cfg = e ? atoi(e) : 9; }
     if (cfg == 0) return launch_cfg<128, 128, 16, 64, 32, 4, TA, TB, AL16, 1>(p, st);
     if (cfg == 1) return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
     if (cfg == 2) return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st);
-    if (TA) return launch_cfg<128, 128, 32, 64, 32, 3, TA, TB, AL16, 1>(p, st);
+    if (cfg == 3) return launch_cfg<128, 64, 16, 64, 32, 3, TA, TB, AL16, 2>(p, st);   // 3 stages: two CTAs/SM also when both tiles are K-contiguous
+    // op(A) K-contiguous: the 4-stage ring of the 128x64 tile is 123 KB, one CTA per SM only (25.9 TFLOP/s); with 3
+    // stages (92 KB) two CTAs fit again: 31.6 TFLOP/s on the SYRK-shaped k = 1024 update against 30.1 for the
+    // 128x128x32 single-CTA tile that used to be selected here
+    if (TA) return launch_cfg<128, 64, 16, 64, 32, 3, TA, TB, AL16, 2>(p, st);
     return launch_cfg<128, 64, 16, 64, 32, 4, TA, TB, AL16, 2>(p, st);
   }
   if (p.N <= 32 || p.M <= 32) {
