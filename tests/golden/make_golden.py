@@ -59,3 +59,30 @@ for i, n in enumerate([5, 32, 97, 140]):
 
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hotpath_golden.npz"), **out)
 print("wrote", len(out), "arrays")
+
+# ---------------------------------------------------------------------------------------------------------------
+# second file (added later in round 1, own seed so that the file above stays byte-identical): complex-single GEMM and
+# the "next" rows of SURVEY section 8f -- (mm a t) / (mm t a), solve on triangular and hermitian matrices.
+out2 = {}
+rng2 = np.random.default_rng(20261020)
+for i, (m, n, k, ta, tb) in enumerate([(7, 5, 3, False, False), (33, 17, 29, True, False), (64, 40, 50, False, True), (20, 31, 9, True, True)]):
+    def rc(*s):
+        return (rng2.uniform(-1, 1, s) + 1j * rng2.uniform(-1, 1, s)).astype(np.complex64)
+    a, b, c = rc(*((k, m) if ta else (m, k))), rc(*((n, k) if tb else (k, n))), rc(m, n)
+    alpha, beta = np.complex64(0.7 - 0.2j), np.complex64(1.3 + 0.5j)
+    out2[f"cgemm{i}_a"], out2[f"cgemm{i}_b"], out2[f"cgemm{i}_c"] = a, b, c
+    out2[f"cgemm{i}_flags"] = np.array([ta, tb])
+    out2[f"cgemm{i}_out"] = O.gemm(alpha, a, b, beta, c.copy(), nl, transpose_a=ta, transpose_b=tb)
+for i, (m, k) in enumerate([(6, 4), (40, 23), (150, 70)]):
+    r = rng2.uniform(-1, 1, (m, k))
+    out2[f"syrk{i}_a"] = r
+    out2[f"syrk{i}_aat"], out2[f"syrk{i}_ata"] = O.mm_hermitian(r, False, nl), O.mm_hermitian(r, True, nl)
+    t = np.triu(rng2.uniform(-1, 1, (m, m))) + 4 * np.eye(m)
+    b = rng2.uniform(-1, 1, (m, 3))
+    out2[f"trsm{i}_u"], out2[f"trsm{i}_b"] = t, b
+    out2[f"trsm{i}_xu"], out2[f"trsm{i}_xl"] = O.trsm(t, True, b, nl), O.trsm(t.T.copy(), False, b, nl)
+    g = rng2.uniform(0, 1, (m, m))
+    spd = g @ g.T + m * np.eye(m)
+    out2[f"posv{i}_a"], out2[f"posv{i}_x"] = spd, O.solve_hermitian(spd, b, nl)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "nextrows_golden.npz"), **out2)
+print("wrote", len(out2), "arrays (next rows)")

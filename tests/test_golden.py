@@ -88,3 +88,52 @@ def test_cuda_factorisations_match_golden():
         assert np.allclose(L.solve(c, G[f"chol{i}_b"]), G[f"chol{i}_x"], rtol=1e-9, atol=1e-12)
     assert np.allclose(L.cholesky(G["ref_chol_a"]).left, G["ref_chol_l"], atol=1e-6)
     assert np.array_equal(L.mm(G["ref_mm_a"], np.array([1.0, 2.0])), [5, 11, 17])
+
+
+# ------------------------------------------------------------------ second fixture file: CGEMM and the "next" rows
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nextrows_golden.npz"))
+CAB = (np.complex64(0.7 - 0.2j), np.complex64(1.3 + 0.5j))
+
+
+def _cgemm_tol(i):
+    a, b = G2[f"cgemm{i}_a"], G2[f"cgemm{i}_b"]
+    ta, tb = (bool(v) for v in G2[f"cgemm{i}_flags"])
+    opa = np.abs(a.conj().T if ta else a).astype(np.float64)
+    opb = np.abs(b.conj().T if tb else b).astype(np.float64)
+    k = 4 * (16 + 4 * np.sqrt(opa.shape[1]))
+    return (k * EPS["s"] * abs(CAB[0]) * np.linalg.norm(opa, axis=1)[:, None] * np.linalg.norm(opb, axis=0)[None, :]
+            + 8 * EPS["s"] * (abs(CAB[1]) * np.abs(G2[f"cgemm{i}_c"]) + np.abs(G2[f"cgemm{i}_out"])))
+
+
+def test_oracle_reproduces_nextrows_goldens():
+    for be in (O.netlib(), O.openblas()):
+        for i in range(4):
+            ta, tb = (bool(v) for v in G2[f"cgemm{i}_flags"])
+            got = O.gemm(CAB[0], G2[f"cgemm{i}_a"], G2[f"cgemm{i}_b"], CAB[1], G2[f"cgemm{i}_c"].copy(), be, transpose_a=ta, transpose_b=tb)
+            assert np.all(np.abs(got - G2[f"cgemm{i}_out"]) <= _cgemm_tol(i))
+        for i in range(3):
+            a = G2[f"syrk{i}_a"]
+            assert np.allclose(O.mm_hermitian(a, False, be), G2[f"syrk{i}_aat"], atol=1e-12)
+            assert np.allclose(O.mm_hermitian(a, True, be), G2[f"syrk{i}_ata"], atol=1e-12)
+            u, b = G2[f"trsm{i}_u"], G2[f"trsm{i}_b"]
+            assert np.allclose(O.trsm(u, True, b, be), G2[f"trsm{i}_xu"], rtol=1e-9, atol=1e-12)
+            assert np.allclose(O.trsm(u.T.copy(), False, b, be), G2[f"trsm{i}_xl"], rtol=1e-9, atol=1e-12)
+            assert np.allclose(O.solve_hermitian(G2[f"posv{i}_a"], b, be), G2[f"posv{i}_x"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_nextrows_match_golden():
+    from lla_b200 import lla as L
+    for i in range(4):
+        ta, tb = (bool(v) for v in G2[f"cgemm{i}_flags"])
+        got = L.gemm(CAB[0], G2[f"cgemm{i}_a"], G2[f"cgemm{i}_b"], CAB[1], G2[f"cgemm{i}_c"].copy(), transpose_a=ta, transpose_b=tb)
+        assert got.dtype == np.complex64
+        assert np.all(np.abs(got.astype(np.complex128) - G2[f"cgemm{i}_out"]) <= _cgemm_tol(i))
+    for i in range(3):
+        a = G2[f"syrk{i}_a"]
+        assert np.allclose(L.mm(a, True).as_array(), G2[f"syrk{i}_aat"], atol=1e-12)
+        assert np.allclose(L.mm(True, a).as_array(), G2[f"syrk{i}_ata"], atol=1e-12)
+        u, b = G2[f"trsm{i}_u"], G2[f"trsm{i}_b"]
+        assert np.allclose(L.solve(L.UpperTriangular(u), b), G2[f"trsm{i}_xu"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(L.solve(L.LowerTriangular(u.T.copy()), b), G2[f"trsm{i}_xl"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(L.solve(L.Hermitian(G2[f"posv{i}_a"]), b), G2[f"posv{i}_x"], rtol=1e-9, atol=1e-12)
