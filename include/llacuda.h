@@ -192,6 +192,22 @@ void dposv_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, dou
 void llacuda_dposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda,
                    double* b, const llacuda_int* ldb, llacuda_int* info);
 
+/* Row-major-native entry points (host pointers; SURVEY section 8b Option B): LLA's row-major arrays as they are, the
+ * layout conversion runs on the device (HBM-bound transpose) instead of the element-wise Lisp loops of
+ * src/foreign-memory.lisp:211-255, and operands LLA marks input-only are never sent back.  lda / ldb are ROW widths.
+ *   llacuda_dgetrf_rm : lu              src/linear-algebra.lisp:225-234   (a: m x n row-major, overwritten by LU)
+ *   llacuda_dgesv_rm  : solve (a b)     src/linear-algebra.lisp:278-289   (a input-only, b: n x nrhs row-major -> x)
+ *   llacuda_dgetrs_rm : solve (lu b)    src/linear-algebra.lisp:264-276   (lu, ipiv input-only)
+ *   llacuda_dpotrs_rm : solve (chol b)  src/linear-algebra.lisp:291-301   (row-major lower factor input-only) */
+void llacuda_dgetrf_rm(const llacuda_int* m, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* ipiv,
+                       llacuda_int* info);
+void llacuda_dgesv_rm(const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda, double* b,
+                      const llacuda_int* ldb, llacuda_int* info);
+void llacuda_dgetrs_rm(const llacuda_int* n, const llacuda_int* nrhs, const double* lu, const llacuda_int* lda,
+                       const llacuda_int* ipiv, double* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_dpotrs_rm(const llacuda_int* n, const llacuda_int* nrhs, const double* l, const llacuda_int* lda, double* b,
+                       const llacuda_int* ldb, llacuda_int* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -714,6 +714,156 @@ LLA_EXPORT void llacuda_dposv(const char* uplo, const fint* n, const fint* nrhs,
   dposv_(uplo, n, nrhs, a, lda, b, ldb, info);
 }
 
+// ------------------------------------------------------------------ row-major-native entry points
+// SURVEY section 8b (Option B, "richer entry points") / 8f rank 1.  LLA's arrays are row-major; for lu / solve the
+// reference converts them with element-wise Lisp loops on both sides of the FFI call (transpose-matrix-to/from-memory,
+// src/foreign-memory.lisp:211-255 -- "today's hidden hot loop").  These entry points take the row-major buffers as they
+// are (host pointers): the conversion is an HBM-bound transpose on the device, and operands that LLA marks input-only
+// (A of `solve`, the factors of `solve` on an lu / cholesky object) are never sent back.
+// A row-major r x c array with row width ld is the column-major c x r matrix with leading dimension ld.
+struct RowMajorIn {
+  Staged raw, cm;   // raw: the bytes as uploaded (column-major c x r); cm: the r x c column-major matrix
+  int upload(int64_t r, int64_t c, const double* host, int64_t ld, cudaStream_t st) {
+    LLA_TRY(stage_alloc(raw, c, r, sizeof(double)));
+    LLA_TRY(stage_alloc(cm, r, c, sizeof(double)));
+    LLA_TRY(stage_upload(raw, host, ld, st));
+    return dtranspose_dev(c, r, raw.ptr<double>(), raw.ld, cm.ptr<double>(), cm.ld, st);
+  }
+  int download(int64_t r, int64_t c, double* host, int64_t ld, cudaStream_t st) {
+    LLA_TRY(dtranspose_dev(r, c, cm.ptr<double>(), cm.ld, raw.ptr<double>(), raw.ld, st));
+    return stage_download(raw, host, ld, st);
+  }
+};
+
+/* lu on a row-major array: reference src/linear-algebra.lisp:225-234 without the two Lisp transposes */
+LLA_EXPORT void llacuda_dgetrf_rm(const fint* m_, const fint* n_, double* a, const fint* lda_, fint* ipiv, fint* info) {
+  ApiLock api_lock;
+  const int64_t m = *m_, n = *n_, lda = *lda_;
+  *info = 0;
+  if (m < 0) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (m == 0 || n == 0) return;
+  Context* cx = ctx();
+  if (!cx) { *info = LLACUDA_ERR_NO_DEVICE; return; }
+  cudaStream_t st = cx->stream;
+  auto run = [&]() -> int {
+    RowMajorIn A;
+    PoolBuf piv, inf;
+    const int64_t mn = m < n ? m : n;
+    LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(mn)));
+    LLA_TRY(inf.alloc(sizeof(int)));
+    LLA_TRY(A.upload(m, n, a, lda, st));
+    LLA_TRY(dgetrf_dev(m, n, A.cm.ptr<double>(), A.cm.ld, (int*)piv.p, (int*)inf.p, st));
+    LLA_TRY(A.download(m, n, a, lda, st));
+    IntOut pivots(ipiv, mn), inf_out(info, 1);
+    LLA_CUDA(cudaMemcpyAsync(pivots.host32(), piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
+    LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LLA_CUDA(cudaStreamSynchronize(st));
+    pivots.finish(); inf_out.finish();
+    return 0;
+  };
+  int rc = run();
+  if (rc != 0) *info = rc;
+}
+
+/* solve on raw row-major arrays: reference src/linear-algebra.lisp:278-289; A is input-only there (&array-in), the
+ * factors and pivots are discarded, so nothing but X travels back */
+LLA_EXPORT void llacuda_dgesv_rm(const fint* n_, const fint* nrhs_, const double* a, const fint* lda_, double* b,
+                                 const fint* ldb_, fint* info) {
+  ApiLock api_lock;
+  const int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  *info = 0;
+  if (n < 0) { *info = -1; return; }
+  if (nrhs < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (ldb < max1(nrhs)) { *info = -6; return; }
+  if (n == 0 || nrhs == 0) return;
+  Context* cx = ctx();
+  if (!cx) { *info = LLACUDA_ERR_NO_DEVICE; return; }
+  cudaStream_t st = cx->stream;
+  auto run = [&]() -> int {
+    RowMajorIn A, B;
+    PoolBuf piv, inf;
+    LLA_TRY(piv.alloc(sizeof(int) * (size_t)n));
+    LLA_TRY(inf.alloc(sizeof(int)));
+    LLA_TRY(A.upload(n, n, a, lda, st));
+    LLA_TRY(B.upload(n, nrhs, b, ldb, st));
+    LLA_TRY(dgetrf_dev(n, n, A.cm.ptr<double>(), A.cm.ld, (int*)piv.p, (int*)inf.p, st));
+    LLA_TRY(dgetrs_dev(0, n, nrhs, A.cm.ptr<double>(), A.cm.ld, (const int*)piv.p, B.cm.ptr<double>(), B.cm.ld, st,
+                       (const int*)inf.p));
+    LLA_TRY(B.download(n, nrhs, b, ldb, st));   // untouched B comes back when INFO > 0 (the solve was skipped)
+    IntOut inf_out(info, 1);
+    LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LLA_CUDA(cudaStreamSynchronize(st));
+    inf_out.finish();
+    return 0;
+  };
+  int rc = run();
+  if (rc != 0) *info = rc;
+}
+
+/* solve on an lu object: reference src/linear-algebra.lisp:264-276; LU (row-major, as LLA stores it) and ipiv are inputs */
+LLA_EXPORT void llacuda_dgetrs_rm(const fint* n_, const fint* nrhs_, const double* lu, const fint* lda_, const fint* ipiv,
+                                  double* b, const fint* ldb_, fint* info) {
+  ApiLock api_lock;
+  const int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  *info = 0;
+  if (n < 0) { *info = -1; return; }
+  if (nrhs < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (ldb < max1(nrhs)) { *info = -7; return; }
+  if (n == 0 || nrhs == 0) return;
+  Context* cx = ctx();
+  if (!cx) { *info = LLACUDA_ERR_NO_DEVICE; return; }
+  cudaStream_t st = cx->stream;
+  auto run = [&]() -> int {
+    RowMajorIn A, B;
+    PoolBuf piv;
+    LLA_TRY(piv.alloc(sizeof(int) * (size_t)n));
+    IntIn pivots(ipiv, n);
+    LLA_CUDA(cudaMemcpyAsync(piv.p, pivots.host32(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    LLA_TRY(A.upload(n, n, lu, lda, st));
+    LLA_TRY(B.upload(n, nrhs, b, ldb, st));
+    LLA_TRY(dgetrs_dev(0, n, nrhs, A.cm.ptr<double>(), A.cm.ld, (const int*)piv.p, B.cm.ptr<double>(), B.cm.ld, st));
+    LLA_TRY(B.download(n, nrhs, b, ldb, st));
+    LLA_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  int rc = run();
+  if (rc != 0) *info = rc;
+}
+
+/* solve on a cholesky object: reference src/linear-algebra.lisp:291-301; the row-major lower factor is shared as it is
+ * (POTRS 'U' of its column-major view), only B needs the layout change */
+LLA_EXPORT void llacuda_dpotrs_rm(const fint* n_, const fint* nrhs_, const double* l, const fint* lda_, double* b,
+                                  const fint* ldb_, fint* info) {
+  ApiLock api_lock;
+  const int64_t n = *n_, nrhs = *nrhs_, lda = *lda_, ldb = *ldb_;
+  *info = 0;
+  if (n < 0) { *info = -1; return; }
+  if (nrhs < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (ldb < max1(nrhs)) { *info = -6; return; }
+  if (n == 0 || nrhs == 0) return;
+  Context* cx = ctx();
+  if (!cx) { *info = LLACUDA_ERR_NO_DEVICE; return; }
+  cudaStream_t st = cx->stream;
+  auto run = [&]() -> int {
+    Staged sa;
+    RowMajorIn B;
+    LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+    LLA_TRY(stage_upload_tri(sa, l, lda, true, st));
+    LLA_TRY(B.upload(n, nrhs, b, ldb, st));
+    LLA_TRY(dpotrs_dev(true, n, nrhs, sa.ptr<double>(), sa.ld, B.cm.ptr<double>(), B.cm.ld, st));
+    LLA_TRY(B.download(n, nrhs, b, ldb, st));
+    LLA_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  int rc = run();
+  if (rc != 0) *info = rc;
+}
+
 // ------------------------------------------------------------------ ZGEMM
 static int zgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuDoubleComplex alpha,
                       const cuDoubleComplex* a, int64_t lda, const cuDoubleComplex* b, int64_t ldb,

@@ -219,11 +219,27 @@ class LU:
         self.lu, self.ipiv_internal = lu, ipiv_internal
 
 
-def lu(a) -> LU:
-    """reference src/linear-algebra.lisp:225-234: GETRF on a transposed copy; INFO>0 ignored."""
+def _native_fn(name):
+    f = getattr(_lib.lib(), name)
+    f.restype = None
+    return f
+
+
+def lu(a, native=False) -> LU:
+    """reference src/linear-algebra.lisp:225-234: GETRF on a transposed copy; INFO>0 ignored.
+    native=True: the row-major array goes to llacuda_dgetrf_rm as it is (layout conversion on the device)."""
     a = np.asarray(a)
     t = common_float_type(a)
     a0, a1 = a.shape
+    if native:
+        if t != DOUBLE:
+            raise NotImplementedError("row-major-native entry points are double precision only")
+        mem = np.array(a, dtype=np.float64, order="C", copy=True)
+        ipiv_internal = np.zeros(min(a0, a1), dtype=np.int32)
+        info = ctypes.c_int(0)
+        _native_fn("llacuda_dgetrf_rm")(_int(a0), _int(a1), _ptr(mem), _int(a1), _ptr(ipiv_internal), ctypes.byref(info))
+        _check_info(info.value, None)
+        return LU(mem, ipiv_internal)
     mem = _transposed_to_memory(a, t)
     ipiv_internal = np.zeros(min(a0, a1), dtype=np.int32)
     info = ctypes.c_int(0)
@@ -239,8 +255,40 @@ class Cholesky:
         self.left = left
 
 
-def solve(a, b):
-    """reference src/linear-algebra.lisp:257-301, dispatching on the class of A like the generic function."""
+def _solve_native(a, b):
+    """solve through the row-major-native entry points: no host-side transposes, input-only operands stay put."""
+    b = np.asarray(b)
+    b0, b1, _ = dimensions_as_matrix(b, "column")
+    x = np.array(b, dtype=np.float64, order="C", copy=True).reshape(b0, b1)
+    info = ctypes.c_int(0)
+    if isinstance(a, LU):
+        n0, n1 = a.lu.shape
+        if not (n0 == n1 == b0):
+            raise LlaIncompatibleDimensions()
+        lu_ = np.ascontiguousarray(a.lu, dtype=np.float64)
+        _native_fn("llacuda_dgetrs_rm")(_int(n0), _int(b1), _ptr(lu_), _int(n0), _ptr(a.ipiv_internal), _ptr(x), _int(b1),
+                                        ctypes.byref(info))
+    elif isinstance(a, Cholesky):
+        l = np.ascontiguousarray(a.left, dtype=np.float64)
+        n0, n1 = l.shape
+        if not (n0 == n1 == b0):
+            raise LlaIncompatibleDimensions()
+        _native_fn("llacuda_dpotrs_rm")(_int(n0), _int(b1), _ptr(l), _int(n0), _ptr(x), _int(b1), ctypes.byref(info))
+    else:
+        am = np.ascontiguousarray(a, dtype=np.float64)
+        n0, n1 = am.shape
+        if not (n0 == n1 == b0):
+            raise LlaIncompatibleDimensions()
+        _native_fn("llacuda_dgesv_rm")(_int(n0), _int(b1), _ptr(am), _int(n0), _ptr(x), _int(b1), ctypes.byref(info))
+    _check_info(info.value)
+    return x.reshape(b.shape)
+
+
+def solve(a, b, native=False):
+    """reference src/linear-algebra.lisp:257-301, dispatching on the class of A like the generic function.
+    native=True (double precision): the row-major-native entry points of include/llacuda.h."""
+    if native and not isinstance(a, (Hermitian, LowerTriangular, UpperTriangular, DeviceLU, DeviceCholesky)):
+        return _solve_native(a, b)
     if isinstance(a, Hermitian):
         return solve_hermitian(a, b)
     if isinstance(a, LowerTriangular):

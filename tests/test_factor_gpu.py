@@ -407,3 +407,29 @@ def test_mm_hermitian_trsm_posv_vs_oracle(m, k):
     spd = g @ g.T + m * np.eye(m)
     x = L.solve(L.Hermitian(spd), b)
     assert residual(spd, x, b) <= 10
+
+
+# ------------------------------------------------------------------ row-major-native entry points
+@pytest.mark.parametrize("n", [5, 257, 1300])
+def test_row_major_native_entry_points_match_the_fortran_path(n):
+    """llacuda_dgetrf_rm / dgesv_rm / dgetrs_rm / dpotrs_rm take LLA's row-major arrays as they are: same kernels on
+    the same numbers as the Fortran-symbol path behind LLA's transposing copies, so the results are identical."""
+    rng = np.random.default_rng(3 * n)
+    a = rng.uniform(0, 10, (n, n))
+    b = rng.uniform(0, 10, (n, 4))
+    f, fn = L.lu(a), L.lu(a, native=True)
+    assert np.array_equal(fn.ipiv_internal, f.ipiv_internal) and np.array_equal(fn.lu, f.lu)
+    r = rng.uniform(0, 10, (n, n + 3))
+    fr, frn = L.lu(r), L.lu(r, native=True)
+    assert np.array_equal(frn.ipiv_internal, fr.ipiv_internal) and np.array_equal(frn.lu, fr.lu)
+    a_keep = a.copy()
+    for rhs in (b, b[:, 0]):
+        assert np.array_equal(L.solve(a, rhs, native=True), L.solve(a, rhs))
+        assert np.array_equal(L.solve(f, rhs, native=True), L.solve(f, rhs))
+    assert np.array_equal(a, a_keep), "A is input-only"
+    spd = a @ a.T + n * np.eye(n)
+    c = L.cholesky(spd)
+    assert np.array_equal(L.solve(c, b, native=True), L.solve(c, b))
+    with pytest.raises(L.LapackFailure) as e:
+        L.solve(np.full((2, 2), 0.5), np.ones(2), native=True)
+    assert e.value.info == 2
