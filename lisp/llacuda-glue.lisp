@@ -115,3 +115,27 @@ routines the device library implements.  Same argument list, same void return, s
 ;;; staged through llacuda_memcpy_h2d / llacuda_dtranspose_dev instead of TRANSPOSE-MATRIX-TO-MEMORY
 ;;; (src/foreign-memory.lisp:211-230).  The method bodies follow the host methods line by line and
 ;;; are left to the maintainer who can run them; the C side is complete and tested.
+
+;;;; --- linear-algebra.lisp: row-major-native entry points (SURVEY 8b Option B) -----------------------------
+;;; The reference transposes A (and B, X) element by element in Lisp on both sides of the call
+;;; (src/foreign-memory.lisp:211-255).  llacuda_dgesv_rm / llacuda_dgetrf_rm / llacuda_dgetrs_rm /
+;;; llacuda_dpotrs_rm take the row-major buffers as they are -- every argument a pointer, INFO by pointer, exactly
+;;; like the Fortran symbols -- so the method is the reference's LAPACK-CALL form minus the :TRANSPOSE? flags.
+;;; Sketch for (solve array array), reference src/linear-algebra.lisp:278-289 (again written blind):
+;;;
+;;;   (defmethod solve ((a array) (b array))
+;;;     (let+ (((a0 a1) (array-dimensions a))
+;;;            ((&values b0 b1 &ign) (dimensions-as-matrix b :column)))
+;;;       (assert (= a0 a1 b0) () 'lla-incompatible-dimensions)
+;;;       (if (and *llacuda-enabled* (eq (common-float-type a b) +double+) (>= a0 *llacuda-min-dimension*))
+;;;           (let ((x (copy-array b)))              ; B is input, X a fresh array: one plain copy, no transpose
+;;;             (with-pinned-array (pa a) (with-pinned-array (px x)
+;;;               (with-fortran-atoms ((n a0) (nrhs b1) (lda a1) (ldb b1) (info 0))
+;;;                 (cffi:foreign-funcall "llacuda_dgesv_rm" :pointer n :pointer nrhs :pointer pa :pointer lda
+;;;                                       :pointer px :pointer ldb :pointer info :void)
+;;;                 (llacuda-check-info (mem-ref info :int32))   ; then the reference's INFO -> condition mapping
+;;;                 x))))
+;;;           (call-next-method))))
+;;;
+;;; Measured through the ctypes mirror of this binding (lla_b200/lla.py, native=True) on B200, n = 8192, 64 right-hand
+;;; sides: 97.5 ms against 1412 ms for the transposing path, identical X (tools/resident_probe.py).
