@@ -149,3 +149,45 @@ def test_block_column_lu_two_ranks(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29545", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+GRID22_SCRIPT = """
+import sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from lla_b200 import dist as LD
+dist.init_process_group("gloo")
+ops = LD.TorchOps()
+grid = LD.make_grid(2, 2)
+nb = 2
+n = nb * 2 * 5                     # 10 blocks per dimension: every process owns diagonal and off-diagonal blocks
+torch.manual_seed(3)
+G = torch.rand((n, n), dtype=torch.float64)
+S = G @ G.t() + n * torch.eye(n, dtype=torch.float64)
+lay = LD.BlockCyclic(n, n, nb, grid)
+for look in (True, False):
+    A_loc = lay.scatter_from_global(torch.triu(S).t().contiguous())
+    assert LD.pdpotrf(grid, n, nb, A_loc, ops, lookahead=look) == 0
+    U = torch.triu(lay.gather_to_global(A_loc).t())
+    assert torch.allclose(U, torch.linalg.cholesky(S).t(), atol=1e-11), look
+b = torch.rand((n, 3), dtype=torch.float64)
+B = b.t().contiguous().clone()
+LD.pdpotrs(grid, n, nb, A_loc, B, ops)
+assert torch.allclose(S @ B.t(), b, atol=1e-10)
+# SUMMA on the same 2 x 2 grid
+A = torch.rand((n, n), dtype=torch.float64); Bm = torch.rand((n, n), dtype=torch.float64)
+C_loc = torch.zeros((n // 2, n // 2), dtype=torch.float64)
+LD.summa(grid, n, n, n, nb, lay.scatter_from_global(A), lay.scatter_from_global(Bm), C_loc, local_gemm=LD.torch_gemm)
+assert torch.allclose(lay.gather_to_global(C_loc), (A.t() @ Bm.t()).t(), atol=1e-12)
+dist.destroy_process_group()
+"""
+
+
+def test_two_by_two_grid_four_ranks(tmp_path):
+    script = tmp_path / "grid22.py"
+    script.write_text(GRID22_SCRIPT.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
+                       capture_output=True, text=True, env=env, timeout=400)
+    assert r.returncode == 0, r.stderr[-3000:]
