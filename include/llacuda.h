@@ -192,6 +192,18 @@ void dposv_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, dou
 void llacuda_dposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda,
                    double* b, const llacuda_int* ldb, llacuda_int* info);
 
+/* the invert family: invert (lu) src/linear-algebra.lisp:358-367 (LWORK = -1 is the size
+ * query of lapack-call-w/query), invert (cholesky) :399-406, invert-triangular% :381-391 */
+void dgetri_(const llacuda_int* n, double* a, const llacuda_int* lda, const llacuda_int* ipiv, double* work,
+             const llacuda_int* lwork, llacuda_int* info);
+void llacuda_dgetri(const llacuda_int* n, double* a, const llacuda_int* lda, const llacuda_int* ipiv, double* work,
+                    const llacuda_int* lwork, llacuda_int* info);
+void dpotri_(const char* uplo, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_dpotri(const char* uplo, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* info);
+void dtrtri_(const char* uplo, const char* diag, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_dtrtri(const char* uplo, const char* diag, const llacuda_int* n, double* a, const llacuda_int* lda,
+                    llacuda_int* info);
+
 /* Row-major-native entry points (host pointers; SURVEY section 8b Option B): LLA's row-major arrays as they are, the
  * layout conversion runs on the device (HBM-bound transpose) instead of the element-wise Lisp loops of
  * src/foreign-memory.lisp:211-255, and operands LLA marks input-only are never sent back.  lda / ldb are ROW widths.

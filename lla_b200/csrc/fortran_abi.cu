@@ -714,6 +714,141 @@ LLA_EXPORT void llacuda_dposv(const char* uplo, const fint* n, const fint* nrhs,
   dposv_(uplo, n, nrhs, a, lda, b, ldb, info);
 }
 
+// ------------------------------------------------------------------ the invert family
+// GETRI / POTRI / TRTRI as solves against the identity on the GEMM-only triangular solvers: (invert lu),
+// (invert cholesky), (invert triangular), reference src/linear-algebra.lisp:352-409.  2 n^3 flop instead of LAPACK's
+// 4/3 n^3, all of it on the DMMA GEMM.
+__global__ void lla_dlacpy_tri_kernel(int64_t n, const double* __restrict__ src, int64_t lds, double* __restrict__ dst,
+                                      int64_t ldd, bool upper, bool skip_diag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= n) return;
+  const bool in_tri = upper ? (i <= j) : (i >= j);
+  if (!in_tri || (skip_diag && i == j)) return;
+  dst[i + j * ldd] = src[i + j * lds];
+}
+
+static int lacpy_tri(int64_t n, const Staged& src, Staged& dst, bool upper, bool skip_diag, cudaStream_t st) {
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  lla_dlacpy_tri_kernel<<<grid, 256, 0, st>>>(n, (const double*)src.buf.p, src.ld, (double*)dst.buf.p, dst.ld, upper, skip_diag);
+  count_launch();
+  LLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int set_identity(Staged& s, int64_t n, cudaStream_t st) {
+  LLA_CUDA(cudaMemset2DAsync(s.buf.p, (size_t)s.ld * 8, 0, (size_t)n * 8, (size_t)n, st));
+  std::vector<double> ones((size_t)n, 1.0);   // pageable source: the copy is staged before the call returns
+  LLA_CUDA(cudaMemcpy2DAsync(s.buf.p, (size_t)(s.ld + 1) * 8, ones.data(), 8, 8, (size_t)n, cudaMemcpyHostToDevice, st));
+  LLA_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int dgetri_host(int64_t n, double* a, int64_t lda, const fint* ipiv) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  Staged sa, sb;
+  PoolBuf piv;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, n, n, sizeof(double)));
+  LLA_TRY(piv.alloc(sizeof(int) * (size_t)n));
+  IntIn pivots(ipiv, n);
+  LLA_CUDA(cudaMemcpyAsync(piv.p, pivots.host32(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+  LLA_TRY(stage_upload(sa, a, lda, st));
+  LLA_TRY(set_identity(sb, n, st));
+  LLA_TRY(dgetrs_dev(0, n, n, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st));
+  LLA_TRY(stage_download(sb, a, lda, st));
+  LLA_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* reference call site: invert (lu), src/linear-algebra.lisp:358-367 (lapack-call-w/query: LWORK = -1 asks for the size) */
+LLA_EXPORT void dgetri_(const fint* n_, double* a, const fint* lda_, const fint* ipiv, double* work, const fint* lwork_,
+                        fint* info) {
+  ApiLock api_lock;
+  const int64_t n = *n_, lda = *lda_, lwork = *lwork_;
+  *info = 0;
+  if (n < 0) { *info = -1; return; }
+  if (lda < max1(n)) { *info = -3; return; }
+  if (lwork < max1(n) && lwork != -1) { *info = -6; return; }
+  work[0] = (double)max1(n);
+  if (lwork == -1 || n == 0) return;
+  for (int64_t i = 0; i < n; i++)
+    if (a[i + i * lda] == 0.0) { *info = (fint)(i + 1); return; }   // U is exactly singular: nothing is computed
+  int rc = dgetri_host(n, a, lda, ipiv);
+  if (rc != 0) *info = rc;
+}
+LLA_EXPORT void llacuda_dgetri(const fint* n, double* a, const fint* lda, const fint* ipiv, double* work, const fint* lwork,
+                               fint* info) {
+  dgetri_(n, a, lda, ipiv, work, lwork, info);
+}
+
+// shared body of POTRI / TRTRI: solve against the identity, copy the named triangle of the result over the factor
+static int tri_inverse_host(bool potri, bool upper, bool unit, int64_t n, double* a, int64_t lda) {
+  Context* cx = ctx();
+  if (!cx) return LLACUDA_ERR_NO_DEVICE;
+  cudaStream_t st = cx->stream;
+  Staged sa, sb;
+  LLA_TRY(stage_alloc(sa, n, n, sizeof(double)));
+  LLA_TRY(stage_alloc(sb, n, n, sizeof(double)));
+  LLA_TRY(stage_upload_tri(sa, a, lda, upper, st));
+  LLA_TRY(set_identity(sb, n, st));
+  if (potri) {
+    LLA_TRY(dpotrs_dev(upper, n, n, sa.ptr<double>(), sa.ld, sb.ptr<double>(), sb.ld, st));
+  } else {
+    Arena ar;
+    LLA_TRY(ar.reserve(tinv_bytes(n) + 1024));
+    double* tinv = (double*)ar.take(tinv_bytes(n));
+    LLA_TRY(dtrtri_blocks_dev(upper, unit, n, sa.ptr<double>(), sa.ld, tinv, st));
+    LLA_TRY(dtrsm_left_inv_dev(upper, 0, n, n, sa.ptr<double>(), sa.ld, tinv, sb.ptr<double>(), sb.ld, st));
+  }
+  LLA_TRY(lacpy_tri(n, sb, sa, upper, !potri && unit, st));
+  LLA_TRY(stage_download_tri(sa, a, lda, upper, 0, st));
+  LLA_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* reference call site: invert (cholesky), src/linear-algebra.lisp:399-406 */
+LLA_EXPORT void dpotri_(const char* uplo, const fint* n_, double* a, const fint* lda_, fint* info) {
+  ApiLock api_lock;
+  const bool upper = (*uplo == 'U' || *uplo == 'u'), lower = (*uplo == 'L' || *uplo == 'l');
+  const int64_t n = *n_, lda = *lda_;
+  *info = 0;
+  if (!upper && !lower) { *info = -1; return; }
+  if (n < 0) { *info = -2; return; }
+  if (lda < max1(n)) { *info = -4; return; }
+  if (n == 0) return;
+  for (int64_t i = 0; i < n; i++)
+    if (a[i + i * lda] == 0.0) { *info = (fint)(i + 1); return; }
+  int rc = tri_inverse_host(true, upper, false, n, a, lda);
+  if (rc != 0) *info = rc;
+}
+LLA_EXPORT void llacuda_dpotri(const char* uplo, const fint* n, double* a, const fint* lda, fint* info) {
+  dpotri_(uplo, n, a, lda, info);
+}
+
+/* reference call site: invert-triangular%, src/linear-algebra.lisp:381-391 */
+LLA_EXPORT void dtrtri_(const char* uplo, const char* diag, const fint* n_, double* a, const fint* lda_, fint* info) {
+  ApiLock api_lock;
+  const bool upper = (*uplo == 'U' || *uplo == 'u'), lower = (*uplo == 'L' || *uplo == 'l');
+  const bool unit = (*diag == 'U' || *diag == 'u'), nonunit = (*diag == 'N' || *diag == 'n');
+  const int64_t n = *n_, lda = *lda_;
+  *info = 0;
+  if (!upper && !lower) { *info = -1; return; }
+  if (!unit && !nonunit) { *info = -2; return; }
+  if (n < 0) { *info = -3; return; }
+  if (lda < max1(n)) { *info = -5; return; }
+  if (n == 0) return;
+  if (nonunit)
+    for (int64_t i = 0; i < n; i++)
+      if (a[i + i * lda] == 0.0) { *info = (fint)(i + 1); return; }
+  int rc = tri_inverse_host(false, upper, unit, n, a, lda);
+  if (rc != 0) *info = rc;
+}
+LLA_EXPORT void llacuda_dtrtri(const char* uplo, const char* diag, const fint* n, double* a, const fint* lda, fint* info) {
+  dtrtri_(uplo, diag, n, a, lda, info);
+}
+
 // ------------------------------------------------------------------ row-major-native entry points
 // SURVEY section 8b (Option B, "richer entry points") / 8f rank 1.  LLA's arrays are row-major; for lu / solve the
 // reference converts them with element-wise Lisp loops on both sides of the FFI call (transpose-matrix-to/from-memory,

@@ -429,6 +429,48 @@ def trsm(a, a_upper: bool, b):
     return x.reshape(b.shape)
 
 
+# ------------------------------------------------------------------ the invert family
+def invert(a):
+    """reference src/linear-algebra.lisp:352-409: arrays through (invert (lu a)) = GETRI with a workspace query,
+    cholesky objects through POTRI('U') -> Hermitian, triangular wrappers through TRTRI (L/U swapped: row-major)."""
+    if isinstance(a, (UpperTriangular, LowerTriangular)):
+        upper = isinstance(a, UpperTriangular)
+        el = np.asarray(a.elements)
+        a0, a1 = el.shape
+        assert a0 == a1
+        t = common_float_type(el)
+        mem = np.array(el, dtype=_DTYPES[t], order="C", copy=True)
+        info = ctypes.c_int(0)
+        _fn(t, "trtri")(_chr("L" if upper else "U"), _chr("N"), _int(a0), _ptr(mem), _int(a0), ctypes.byref(info))
+        _check_info(info.value)
+        return UpperTriangular(np.triu(mem)) if upper else LowerTriangular(np.tril(mem))
+    if isinstance(a, Cholesky):
+        l = np.asarray(a.left)
+        a0, a1 = l.shape
+        assert a0 == a1
+        t = common_float_type(l)
+        mem = np.array(l, dtype=_DTYPES[t], order="C", copy=True)
+        info = ctypes.c_int(0)
+        _fn(t, "potri")(_chr("U"), _int(a0), _ptr(mem), _int(a0), ctypes.byref(info))
+        _check_info(info.value)
+        return Hermitian(mem)
+    if not isinstance(a, LU):
+        a = lu(a)
+    lu0, lu1 = a.lu.shape
+    assert lu0 == lu1 == len(a.ipiv_internal)
+    t = common_float_type(a.lu)
+    mem = _transposed_to_memory(a.lu, t)
+    info = ctypes.c_int(0)
+    query = np.zeros(1, dtype=_DTYPES[t])
+    _fn(t, "getri")(_int(lu0), _ptr(mem), _int(lu0), _ptr(a.ipiv_internal), _ptr(query), _int(-1), ctypes.byref(info))
+    _check_info(info.value)                      # lapack-call-w/query: first call sizes the work area
+    lwork = max(1, int(query[0].real))
+    work = np.zeros(lwork, dtype=_DTYPES[t])
+    _fn(t, "getri")(_int(lu0), _ptr(mem), _int(lu0), _ptr(a.ipiv_internal), _ptr(work), _int(lwork), ctypes.byref(info))
+    _check_info(info.value)
+    return _transposed_from_memory(mem, (lu0, lu0))
+
+
 # ------------------------------------------------------------------ device-resident factorization objects
 # SURVEY.md section 8f rank 1: the reference re-marshals the factors on every call -- `solve ((lu lu) b)` transposes the
 # stored n x n LU into foreign memory each time (src/linear-algebra.lisp:264-276, src/foreign-memory.lisp:211-255).

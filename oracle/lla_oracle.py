@@ -400,6 +400,35 @@ def trsm(a, a_upper: bool, b, be: Backend):
     return xmem.reshape(b.shape)
 
 
+def invert(a, be: Backend, kind="array"):
+    """src/linear-algebra.lisp:352-409 on a back end that exports the LAPACK inverses (host OpenBLAS): kind = "array"
+    ((invert (lu a)) = GETRF + GETRI with workspace query), "cholesky" (a = row-major lower factor, POTRI 'U'),
+    "upper" / "lower" (TRTRI with L / U swapped)."""
+    a = np.asarray(a)
+    n = a.shape[0]
+    t = common_float_type(a)
+    info = ctypes.c_int(0)
+    if kind in ("upper", "lower"):
+        mem = copy_array_to_memory(a, t)
+        be.fn(t, "trtri")(_chr("L" if kind == "upper" else "U"), _chr("N"), _int(n), _ptr(mem), _int(n), ctypes.byref(info))
+        _check_info(info.value)
+        return np.triu(mem) if kind == "upper" else np.tril(mem)
+    if kind == "cholesky":
+        mem = copy_array_to_memory(a, t)
+        be.fn(t, "potri")(_chr("U"), _int(n), _ptr(mem), _int(n), ctypes.byref(info))
+        _check_info(info.value)
+        low = np.tril(mem)
+        return low + np.tril(mem, -1).T
+    f = lu(a, be)
+    mem = transpose_matrix_to_memory(f.lu, t)
+    query = np.zeros(1, dtype=_DTYPES[t])
+    be.fn(t, "getri")(_int(n), _ptr(mem), _int(n), _ptr(f.ipiv_internal), _ptr(query), _int(-1), ctypes.byref(info))
+    work = np.zeros(max(1, int(query[0].real)), dtype=_DTYPES[t])
+    be.fn(t, "getri")(_int(n), _ptr(mem), _int(n), _ptr(f.ipiv_internal), _ptr(work), _int(work.size), ctypes.byref(info))
+    _check_info(info.value)
+    return transpose_matrix_from_memory(mem, (n, n))
+
+
 # ------------------------------------------------ factorization post-processing
 def ipiv(ipiv_internal) -> np.ndarray:
     """src/factorizations.lisp:15-28: swap sequence -> 0-based permutation."""

@@ -212,3 +212,16 @@ def test_next_rows_backends_agree():
     b = rng.uniform(-1, 1, (30, 4))
     assert np.allclose(O.trsm(t, True, b, O.netlib()), O.trsm(t, True, b, O.openblas()), rtol=1e-10)
     assert np.allclose(O.trsm(t.T.copy(), False, b, O.netlib()), O.trsm(t.T.copy(), False, b, O.openblas()), rtol=1e-10)
+
+
+def test_invert_reference_goldens_on_host_lapack():
+    """tests/linear-algebra.lisp:229-244 (invert) and :366-385 ((invert c) of the cholesky test) on host OpenBLAS -- the
+    LAPACK inverses are not part of the netlib restatement."""
+    be = O.openblas()
+    m = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert np.allclose(O.invert(m, be), [[-2, 1], [1.5, -0.5]], atol=1e-14)
+    assert np.allclose(O.invert(np.triu(m), be, "upper"), [[1, -0.5], [0, 0.25]], atol=1e-14)
+    assert np.allclose(O.invert(np.tril(m), be, "lower"), [[1, 0], [-0.75, 0.25]], atol=1e-14)
+    spd = np.array([[2.0, -1, 0], [-1, 2, -1], [0, -1, 2]])
+    c = O.cholesky(spd, be)
+    assert np.allclose(O.invert(c.left, be, "cholesky"), np.linalg.inv(spd), atol=1e-14)
