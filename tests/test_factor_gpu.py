@@ -464,5 +464,9 @@ def test_invert_vs_oracle(n):
     t = np.triu(rng.uniform(-1, 1, (n, n))) + 4 * np.eye(n)
     ti = L.invert(L.UpperTriangular(t)).elements
     assert np.linalg.norm(t @ ti - np.eye(n)) / (n * EPS * np.linalg.norm(t) * np.linalg.norm(ti)) <= 10
-    li = L.invert(L.LowerTriangular(t.T.copy())).elements
-    assert np.allclose(li, ti.T, rtol=1e-10, atol=1e-13)
+    tl = t.T.copy()
+    li = L.invert(L.LowerTriangular(tl)).elements
+    # (no elementwise comparison with ti.T: the inverse of a random triangular matrix has entries ~1e3-1e4 at n = 1100 and
+    # the forward / backward substitution orders round differently; the scaled residual is the bar, as for the upper case)
+    assert np.all(np.triu(li, 1) == 0.0)
+    assert np.linalg.norm(tl @ li - np.eye(n)) / (n * EPS * np.linalg.norm(tl) * np.linalg.norm(li)) <= 10
