@@ -41,7 +41,7 @@
 ;;; recompiled after this redefinition (asdf:load-system "lla" :force t), or use Option A.
 
 (defparameter *llacuda-routines*
-  '(("D" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs" "syrk" "posv" "trsm"))
+  '(("D" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs" "syrk" "posv" "trsm" "getri" "potri" "trtri"))
     ("S" . ("gemm"))
     ("C" . ("gemm"))
     ("Z" . ("gemm")))
