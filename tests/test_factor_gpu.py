@@ -433,40 +433,3 @@ def test_row_major_native_entry_points_match_the_fortran_path(n):
     with pytest.raises(L.LapackFailure) as e:
         L.solve(np.full((2, 2), 0.5), np.ones(2), native=True)
     assert e.value.info == 2
-
-
-# ------------------------------------------------------------------ the invert family on the device
-def test_invert_reference_goldens():
-    m = np.array([[1.0, 2.0], [3.0, 4.0]])                                   # tests/linear-algebra.lisp:229-244
-    assert num_eq(L.invert(m), [[-2, 1], [1.5, -0.5]])
-    assert num_eq(L.invert(L.lu(m)), [[-2, 1], [1.5, -0.5]])
-    assert num_eq(L.invert(L.UpperTriangular(m)).elements, [[1, -0.5], [0, 0.25]])
-    assert num_eq(L.invert(L.LowerTriangular(m)).elements, [[1, 0], [-0.75, 0.25]])
-    spd = np.array([[2.0, -1, 0], [-1, 2, -1], [0, -1, 2]])                  # :366-385
-    assert num_eq(L.invert(L.cholesky(spd)).as_array(), np.linalg.inv(spd))
-    with pytest.raises(L.LapackFailure) as e:
-        L.invert(np.array([[1.0, 2.0], [2.0, 4.0]]))
-    assert e.value.info == 2
-
-
-@pytest.mark.parametrize("n", [37, 300, 1100])
-def test_invert_vs_oracle(n):
-    rng = np.random.default_rng(9 * n)
-    a = rng.uniform(0, 10, (n, n))
-    inv = L.invert(a)
-    ref = O.invert(a, O.openblas())
-    assert np.linalg.norm(a @ inv - np.eye(n)) / (n * EPS * np.linalg.norm(a) * np.linalg.norm(inv)) <= 10
-    assert np.max(np.abs(inv - ref)) <= 1e-7 * np.abs(ref).max()
-    spd = a @ a.T + n * np.eye(n)
-    ci = L.invert(L.cholesky(spd))
-    assert np.all(np.triu(ci.elements, 1) == np.triu(L.cholesky(spd).left, 1)), "POTRI('U') must leave the other triangle alone"
-    assert np.linalg.norm(spd @ ci.as_array() - np.eye(n)) / (n * EPS * np.linalg.norm(spd) * np.linalg.norm(ci.as_array())) <= 10
-    t = np.triu(rng.uniform(-1, 1, (n, n))) + 4 * np.eye(n)
-    ti = L.invert(L.UpperTriangular(t)).elements
-    assert np.linalg.norm(t @ ti - np.eye(n)) / (n * EPS * np.linalg.norm(t) * np.linalg.norm(ti)) <= 10
-    tl = t.T.copy()
-    li = L.invert(L.LowerTriangular(tl)).elements
-    # (no elementwise comparison with ti.T: the inverse of a random triangular matrix has entries ~1e3-1e4 at n = 1100 and
-    # the forward / backward substitution orders round differently; the scaled residual is the bar, as for the upper case)
-    assert np.all(np.triu(li, 1) == 0.0)
-    assert np.linalg.norm(tl @ li - np.eye(n)) / (n * EPS * np.linalg.norm(tl) * np.linalg.norm(li)) <= 10
