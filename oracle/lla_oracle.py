@@ -401,7 +401,7 @@ def trsm(a, a_upper: bool, b, be: Backend):
 
 
 def invert(a, be: Backend, kind="array"):
-    """src/linear-algebra.lisp:352-409 on a back end that exports the LAPACK inverses (host OpenBLAS): kind = "array"
+    """src/linear-algebra.lisp:352-409 (both back ends export the LAPACK inverses): kind = "array"
     ((invert (lu a)) = GETRF + GETRI with workspace query), "cholesky" (a = row-major lower factor, POTRI 'U'),
     "upper" / "lower" (TRTRI with L / U swapped)."""
     a = np.asarray(a)

@@ -3,7 +3,7 @@
  * CPU oracle for the llacuda hot path: a scalar C restatement of the netlib
  * reference BLAS/LAPACK algorithms behind LLA's FFI call sites, instantiated
  * for LLA's four float types (src/types.lisp:22-26: 0=S 1=D 2=C 3=Z).
- * Symbols: oracle_{s,d,c,z}{gemm,getrf,getrs,gesv,potrf,potrs}_  with the exact
+ * Symbols: oracle_{s,d,c,z}{gemm,getrf,getrs,gesv,potrf,potrs,syrk,trsm,posv,trtri,potri,getri}_  with the exact
  * Fortran pointer-only signatures LLA passes (src/fortran-call.lisp:418-439).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl

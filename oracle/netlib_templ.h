@@ -341,6 +341,87 @@ void PFX(posv_)(const char *uplo, const int *n_, const int *nrhs_, T *a, const i
   if (*info == 0) PFX(potrs_)(uplo, n_, nrhs_, a, lda_, b, ldb_, info);
 }
 
+/* ------------------------------------------------------------------ the invert family
+ * xTRTRI (as xTRTI2) <- invert-triangular%  src/linear-algebra.lisp:381-391
+ * xPOTRI (= xTRTRI + xLAUUM) <- invert (cholesky)  :399-406
+ * xGETRI (unblocked)  <- invert (lu)  :358-367, LWORK = -1 answers the workspace query of lapack-call-w/query */
+void PFX(trtri_)(const char *uplo, const char *diag, const int *n_, T *a, const int *lda_, int *info) {
+  int64_t n = *n_, lda = *lda_;
+  int upper = PFX(lsame)(*uplo, 'U'), nounit = PFX(lsame)(*diag, 'N');
+  *info = 0;
+  if (nounit)
+    for (int64_t i = 0; i < n; i++)
+      if (a[i + i * lda] == (T)0) { *info = (int)(i + 1); return; }
+  if (upper) {
+    for (int64_t j = 0; j < n; j++) {
+      T ajj;
+      if (nounit) { a[j + j * lda] = (T)1 / a[j + j * lda]; ajj = -a[j + j * lda]; } else ajj = -(T)1;
+      /* x = T(0:j,0:j) * a(0:j, j)  (xTRMV upper, no transpose: ascending i reads only not-yet-overwritten entries) */
+      for (int64_t i = 0; i < j; i++) {
+        T s = nounit ? a[i + i * lda] * a[i + j * lda] : a[i + j * lda];
+        for (int64_t l = i + 1; l < j; l++) s += a[i + l * lda] * a[l + j * lda];
+        a[i + j * lda] = s;
+      }
+      for (int64_t i = 0; i < j; i++) a[i + j * lda] *= ajj;
+    }
+  } else {
+    for (int64_t j = n - 1; j >= 0; j--) {
+      T ajj;
+      if (nounit) { a[j + j * lda] = (T)1 / a[j + j * lda]; ajj = -a[j + j * lda]; } else ajj = -(T)1;
+      for (int64_t i = n - 1; i > j; i--) {
+        T s = nounit ? a[i + i * lda] * a[i + j * lda] : a[i + j * lda];
+        for (int64_t l = j + 1; l < i; l++) s += a[i + l * lda] * a[l + j * lda];
+        a[i + j * lda] = s;
+      }
+      for (int64_t i = j + 1; i < n; i++) a[i + j * lda] *= ajj;
+    }
+  }
+}
+
+void PFX(potri_)(const char *uplo, const int *n_, T *a, const int *lda_, int *info) {
+  int64_t n = *n_, lda = *lda_;
+  int upper = PFX(lsame)(*uplo, 'U');
+  char nn = 'N';
+  PFX(trtri_)(uplo, &nn, n_, a, lda_, info);
+  if (*info != 0) return;
+  /* xLAUUM: upper: A <- U U^H, lower: A <- L^H L, in place, only the named triangle */
+  if (upper) {
+    for (int64_t i = 0; i < n; i++)
+      for (int64_t j = i; j < n; j++) {
+        T s = 0;
+        for (int64_t l = j; l < n; l++) s += a[i + l * lda] * CONJ(a[j + l * lda]);
+        a[i + j * lda] = s;      /* row i, ascending j: entries (i, l >= j) are still U's when read */
+      }
+  } else {
+    for (int64_t j = 0; j < n; j++)
+      for (int64_t i = j; i < n; i++) {
+        T s = 0;
+        for (int64_t l = i; l < n; l++) s += CONJ(a[l + i * lda]) * a[l + j * lda];
+        a[i + j * lda] = s;
+      }
+  }
+}
+
+void PFX(getri_)(const int *n_, T *a, const int *lda_, const int *ipiv, T *work, const int *lwork_, int *info) {
+  int64_t n = *n_, lda = *lda_, lwork = *lwork_;
+  *info = 0;
+  work[0] = (T)(n > 1 ? n : 1);
+  if (lwork == -1 || n == 0) return;
+  char uu = 'U', nn = 'N';
+  PFX(trtri_)(&uu, &nn, n_, a, lda_, info);          /* inv(U); INFO > 0: U singular */
+  if (*info > 0) return;
+  for (int64_t j = n - 1; j >= 0; j--) {              /* solve inv(A) L = inv(U), column by column from the right */
+    for (int64_t i = j + 1; i < n; i++) { work[i] = a[i + j * lda]; a[i + j * lda] = 0; }
+    for (int64_t l = j + 1; l < n; l++)
+      for (int64_t i = 0; i < n; i++) a[i + j * lda] -= a[i + l * lda] * work[l];
+  }
+  for (int64_t j = n - 2; j >= 0; j--) {              /* column interchanges undo the row interchanges of the factorisation */
+    int64_t jp = ipiv[j] - 1;
+    if (jp != j)
+      for (int64_t i = 0; i < n; i++) { T tmp = a[i + j * lda]; a[i + j * lda] = a[i + jp * lda]; a[i + jp * lda] = tmp; }
+  }
+}
+
 #undef ABS1
 #undef CONJ
 #undef REAL

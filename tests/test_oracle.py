@@ -214,10 +214,11 @@ def test_next_rows_backends_agree():
     assert np.allclose(O.trsm(t.T.copy(), False, b, O.netlib()), O.trsm(t.T.copy(), False, b, O.openblas()), rtol=1e-10)
 
 
-def test_invert_reference_goldens_on_host_lapack():
-    """tests/linear-algebra.lisp:229-244 (invert) and :366-385 ((invert c) of the cholesky test) on host OpenBLAS -- the
-    LAPACK inverses are not part of the netlib restatement."""
-    be = O.openblas()
+@pytest.mark.parametrize("be", ["netlib", "openblas"])
+def test_invert_reference_goldens(be):
+    """tests/linear-algebra.lisp:229-244 (invert) and :366-385 ((invert c) of the cholesky test), on the netlib
+    restatement (xTRTI2, xLAUUM, unblocked xGETRI with the LWORK = -1 query) and on host OpenBLAS."""
+    be = getattr(O, be)()
     m = np.array([[1.0, 2.0], [3.0, 4.0]])
     assert np.allclose(O.invert(m, be), [[-2, 1], [1.5, -0.5]], atol=1e-14)
     assert np.allclose(O.invert(np.triu(m), be, "upper"), [[1, -0.5], [0, 0.25]], atol=1e-14)
@@ -225,3 +226,18 @@ def test_invert_reference_goldens_on_host_lapack():
     spd = np.array([[2.0, -1, 0], [-1, 2, -1], [0, -1, 2]])
     c = O.cholesky(spd, be)
     assert np.allclose(O.invert(c.left, be, "cholesky"), np.linalg.inv(spd), atol=1e-14)
+
+
+def test_invert_backends_agree():
+    rng = np.random.default_rng(77)
+    a = rng.uniform(0, 10, (60, 60))
+    assert np.allclose(O.invert(a, O.netlib()), O.invert(a, O.openblas()), rtol=1e-9, atol=1e-12)
+    spd = a @ a.T + 60 * np.eye(60)
+    l = O.cholesky(spd, O.netlib()).left
+    assert np.allclose(O.invert(l, O.netlib(), "cholesky"), O.invert(l, O.openblas(), "cholesky"), rtol=1e-9, atol=1e-14)
+    t = np.triu(rng.uniform(-1, 1, (50, 50))) + 4 * np.eye(50)
+    for kind, mat in (("upper", t), ("lower", t.T.copy())):
+        assert np.allclose(O.invert(mat, O.netlib(), kind), O.invert(mat, O.openblas(), kind), rtol=1e-10, atol=1e-14)
+    with pytest.raises(O.LapackFailure) as e:
+        O.invert(np.array([[1.0, 2.0], [2.0, 4.0]]), O.netlib())
+    assert e.value.info == 2

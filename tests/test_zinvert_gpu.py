@@ -38,6 +38,8 @@ def test_invert_vs_oracle(n):
     a = rng.uniform(0, 10, (n, n))
     inv = L.invert(a)
     ref = O.invert(a, O.openblas())
+    if n <= 300:
+        assert np.allclose(O.invert(a, O.netlib()), ref, rtol=1e-8, atol=1e-12)      # the two oracle back ends agree
     assert np.linalg.norm(a @ inv - np.eye(n)) / (n * EPS * np.linalg.norm(a) * np.linalg.norm(inv)) <= 10
     assert np.max(np.abs(inv - ref)) <= 1e-7 * np.abs(ref).max()
     spd = a @ a.T + n * np.eye(n)
