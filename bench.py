@@ -355,7 +355,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ncpu = args.cpu_n or pick_cpu_n(150.0, args.steps + args.warmup)
+        ncpu = args.cpu_n or min(n, pick_cpu_n(150.0, args.steps + args.warmup))   # a bounded sample, never above the workload
         r = cpu_leg(ncpu, args.steps, args.warmup)
         sample = (f"the same three calls (dgemm/dgesv/dpotrf as LLA issues them) at n={ncpu}, nrhs={NRHS}, "
                   f"{args.steps} timed steps after {args.warmup} warm-up; {r['blas']}")
@@ -379,7 +379,7 @@ def main():
     value = total_f / (g["total_ms"] * 1e-3) / 1e9
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
-        ncpu = args.cpu_n or pick_cpu_n(25.0, 2)
+        ncpu = args.cpu_n or min(n, pick_cpu_n(25.0, 2))
         r = cpu_leg(ncpu, 1, 1)
         cpu = {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "port",
                "sample": f"dgemm/dgesv/dpotrf as LLA issues them at n={ncpu}, nrhs={NRHS}, 1 timed pass after 1 warm-up; {r['blas']}",
