@@ -42,6 +42,15 @@ extern "C" {
 /* ------------------------------------------------------------------ runtime / helpers */
 int  llacuda_set_device(int device);           /* before the first call; one device per process */
 int  llacuda_init(void);                       /* 0, or LLACUDA_ERR_NO_DEVICE (no CPU fallback) */
+/* BLAS-style entry points (dgemm_, dsyrk_, dtrsm_, ...) have no INFO argument.  When one of them fails on the device
+ * side (out of memory, launch failure, no device) the library does what netlib's XERBLA does: it prints the reason and
+ * stops the program (mode 0, the default) -- LLA's mm passes a zeroed C with beta = 0, so returning quietly would look
+ * like an all-zero product.  Mode 1 (or LLACUDA_ON_ERROR=return): the output is filled with NaN, the error is recorded
+ * and the call returns; the caller must poll llacuda_last_error_code(), which every such entry point clears on entry.
+ * The handler, if any, runs first in both modes. */
+void llacuda_set_error_mode(int mode);
+int  llacuda_error_mode(void);
+void llacuda_set_error_handler(void (*handler)(const char* routine, int code, const char* message));
 const char* llacuda_last_error(void);
 int  llacuda_last_error_code(void);
 void llacuda_clear_error(void);

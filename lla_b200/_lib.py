@@ -38,6 +38,9 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(SO_PATH)
         _lib.llacuda_last_error.restype = ctypes.c_char_p
         _lib.llacuda_stream.restype = ctypes.c_void_p
+        # BLAS-style entry points: poison the output, record the error and return (the mirror polls
+        # llacuda_last_error_code after every call and raises) instead of the XERBLA-style stop
+        _lib.llacuda_set_error_mode(1)
     return _lib
 
 

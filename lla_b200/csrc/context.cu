@@ -20,7 +20,7 @@ static std::mutex g_mu;
 static std::recursive_mutex g_api_mu;
 ApiLock::ApiLock() { g_api_mu.lock(); }
 ApiLock::~ApiLock() { g_api_mu.unlock(); }
-static Context* g_ctx = nullptr;
+static std::atomic<Context*> g_ctx[MAX_DEV];
 static thread_local char g_err[512] = "";
 static thread_local int g_err_code = 0;
 
@@ -29,7 +29,7 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 
 void set_error(const char* file, int line, const char* what, int code) {
   snprintf(g_err, sizeof(g_err), "%s:%d: %s (code %d)", file, line, what, code);
-  g_err_code = code;
+  g_err_code = code ? code : -1;
 }
 
 int record_cuda_error(cudaError_t e, const char* file, int line) {
@@ -37,16 +37,49 @@ int record_cuda_error(cudaError_t e, const char* file, int line) {
   return LLACUDA_ERR_CUDA_BASE - (int)e;
 }
 
+// ---- failures of the BLAS-style entry points (no INFO argument).  netlib's XERBLA prints and STOPs; LLA's mm hands
+// a zeroed C with beta = 0, so a failure that merely returned would look like an all-zero product.
+static std::atomic<int> g_err_mode{-1};
+static std::atomic<void (*)(const char*, int, const char*)> g_err_handler{nullptr};
+static int err_mode() {
+  int m = g_err_mode.load();
+  if (m < 0) {
+    const char* e = getenv("LLACUDA_ON_ERROR");
+    m = (e && (e[0] == 'r' || e[0] == 'R')) ? 1 : 0;
+    g_err_mode.store(m);
+  }
+  return m;
+}
+void blas_failure(const char* routine, int rc, void* out, int64_t ld, int64_t rows, int64_t cols, size_t es) {
+  drain_streams();
+  if (g_err_code == 0) set_error(__FILE__, __LINE__, "failure in a BLAS-style entry point", rc);
+  fprintf(stderr, " ** llacuda: %s failed (code %d): %s\n", routine, rc, g_err);
+  if (auto h = g_err_handler.load()) h(routine, rc, g_err);
+  if (err_mode() == 0) {
+    fprintf(stderr, " ** llacuda: stopping, as XERBLA would (llacuda_set_error_mode(1) or LLACUDA_ON_ERROR=return: "
+                    "poison the output with NaN, record the error and return)\n");
+    abort();
+  }
+  if (out)   // all-ones bytes are a NaN in every IEEE format: the result cannot be mistaken for a product
+    for (int64_t j = 0; j < cols; j++) memset((char*)out + (size_t)j * ld * es, 0xff, (size_t)rows * es);
+}
+
+int cur_dev() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return dev;
+}
+
 Context* ctx() {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_ctx) return g_ctx;
-  Context* c = new Context();
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) {
+  const int dev = cur_dev();
+  if (dev < 0 || dev >= MAX_DEV) {
     set_error(__FILE__, __LINE__, "no CUDA device: llacuda has no CPU fallback", -1);
-    delete c;
     return nullptr;
   }
+  if (Context* c = g_ctx[dev].load(std::memory_order_acquire)) return c;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (Context* c = g_ctx[dev].load(std::memory_order_acquire)) return c;
+  Context* c = new Context();
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
     set_error(__FILE__, __LINE__, "cudaGetDeviceProperties failed", -1);
@@ -67,31 +100,31 @@ Context* ctx() {
   cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
   for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-  g_ctx = c;
-  return g_ctx;
+  g_ctx[dev].store(c, std::memory_order_release);
+  return c;
 }
 
-int ensure_workspace(size_t bytes) {
-  Context* c = ctx();
-  if (!c) return LLACUDA_ERR_NO_DEVICE;
-  if (c->ws_bytes >= bytes) return 0;
-  if (c->ws) {
-    LLA_CUDA(cudaDeviceSynchronize());
-    LLA_CUDA(cudaFree(c->ws));
-    c->ws = nullptr;
-    c->ws_bytes = 0;
+void drain_streams() {
+  const int dev = cur_dev();
+  if (dev < 0 || dev >= MAX_DEV) return;
+  Context* c = g_ctx[dev].load(std::memory_order_acquire);
+  if (!c) return;
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->aux);
+  cudaStreamSynchronize(c->h2d);
+  cudaStreamSynchronize(c->d2h);
+  cudaGetLastError();
+}
+
+int Arena::reserve(size_t bytes, cudaStream_t st) {
+  if (!ctx()) return LLACUDA_ERR_NO_DEVICE;
+  const size_t want = bytes + 4096;
+  base = (char*)stream_scratch(st, want);
+  if (!base) {
+    set_error(__FILE__, __LINE__, "out of device memory for the per-call scratch", (int)(want >> 20));
+    return LLACUDA_ERR_CUDA_BASE - (int)cudaErrorMemoryAllocation;
   }
-  size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes;
-  LLA_CUDA(cudaMalloc(&c->ws, want));
-  LLA_CUDA(cudaMemset(c->ws, 0, want));  // the panel exchange area must not start with stray tags
-  c->ws_bytes = want;
-  return 0;
-}
-
-int Arena::reserve(size_t bytes) {
-  LLA_TRY(ensure_workspace(bytes + 4096));
-  base = (char*)ctx()->ws;
-  cap = ctx()->ws_bytes;
+  cap = want;
   used = 0;
   return 0;
 }
@@ -120,6 +153,13 @@ void trace_mark(cudaStream_t st, const char* label, long long a, long long b) {
 
 struct StreamBuf { void* p; size_t bytes; };
 static std::vector<std::pair<cudaStream_t, StreamBuf>> g_stream_scratch;
+static void* scratch_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  // the LU panel's exchange area must not start with stray tags
+  if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+  return p;
+}
 void* stream_scratch(cudaStream_t st, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& e : g_stream_scratch) {
@@ -127,18 +167,19 @@ void* stream_scratch(cudaStream_t st, size_t bytes) {
     if (e.second.bytes >= bytes) return e.second.p;
     cudaStreamSynchronize(st);   // the only user of this buffer is work queued on st
     cudaFree(e.second.p);
-    e.second = {nullptr, 0};
-    if (cudaMalloc(&e.second.p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    e.second.bytes = bytes;
+    size_t want = bytes + bytes / 2;
+    e.second = {scratch_alloc(want), want};
+    if (!e.second.p) e.second.bytes = 0;
     return e.second.p;
   }
-  StreamBuf b{nullptr, bytes};
-  if (cudaMalloc(&b.p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  size_t want = bytes < (size_t(1) << 20) ? (size_t(1) << 20) : bytes;
+  StreamBuf b{scratch_alloc(want), want};
+  if (!b.p) return nullptr;
   g_stream_scratch.push_back({st, b});
   return b.p;
 }
 
-static const RowsFinalHook* g_rows_hook = nullptr;
+static thread_local const RowsFinalHook* g_rows_hook = nullptr;
 void set_rows_final_hook(const RowsFinalHook* h) { g_rows_hook = h; }
 const RowsFinalHook* rows_final_hook() { return g_rows_hook; }
 
@@ -161,16 +202,14 @@ const char* llacuda_last_error(void) { return g_err; }
 int llacuda_last_error_code(void) { return g_err_code; }
 void llacuda_clear_error(void) { g_err[0] = 0; g_err_code = 0; }
 
+void llacuda_set_error_mode(int mode) { g_err_mode.store(mode ? 1 : 0); }
+int llacuda_error_mode(void) { return err_mode(); }
+void llacuda_set_error_handler(void (*handler)(const char* routine, int code, const char* message)) { g_err_handler.store(handler); }
+
 unsigned long long llacuda_launch_count(void) { return g_launches.load(); }
 
 int llacuda_set_device(int device) {
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx && g_ctx->device != device) {
-      set_error(__FILE__, __LINE__, "llacuda_set_device: context already bound to another device", g_ctx->device);
-      return LLACUDA_ERR_BAD_ARG;
-    }
-  }
+  // the classic (single-GPU) entry points run on the calling thread's current device; contexts are per device
   LLA_CUDA(cudaSetDevice(device));
   return 0;
 }
@@ -189,18 +228,17 @@ int llacuda_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* tot
   return 0;
 }
 
-static cudaStream_t g_own_stream = nullptr;
 int llacuda_set_stream(void* cuda_stream) {
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
-  if (!g_own_stream) g_own_stream = c->stream;
+  if (!c->own_stream) c->own_stream = c->stream;
   c->stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream, a valid choice
   return 0;
 }
 int llacuda_reset_stream(void) {
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
-  if (g_own_stream) c->stream = g_own_stream;
+  if (c->own_stream) c->stream = c->own_stream;
   return 0;
 }
 

@@ -15,7 +15,6 @@ using namespace llacuda;
 #define LLA_EXPORT extern "C"
 
 static int opcode(char c) {
-  ApiLock api_lock;
   switch (c) {
     case 'N': case 'n': return 0;
     case 'T': case 't': return 1;
@@ -69,65 +68,80 @@ static int dgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, double al
     tm.mark(2);
     LLA_TRY(stage_download(sc, c, ldc, st));
     tm.mark(3);
-    LLA_CUDA(cudaStreamSynchronize(st));
+    LLA_TRY(stage_sync(st));
     tm.finish();
     return 0;
   }
-  // 2-D pipeline: op(A) = A is cut into RC row blocks, op(B) = B / C into `chunks` column blocks.  Uploads are queued
-  // as A_0, B_0 .. B_last, A_1 ..; block (r, c) of C is computed as soon as A_r and B_c (and C_rc when beta != 0)
-  // have arrived and goes back at once, so only A_0 + B_0 on the way in and the last block on the way out are
-  // exposed.  Each GEMM keeps >= ~7 waves of 128x64 tiles so that the per-launch tail stays around 1 %.
+  // 2-D pipeline: op(A) = A is cut into RC row blocks, op(B) = B / C into `chunks` column blocks; block (r, c) of C
+  // is computed as soon as A_r and B_c (and C_rc when beta != 0) have arrived and goes back at once, so only A_0 + B_0
+  // on the way in and the last block on the way out are exposed.  The operands of block i+1 are queued right after
+  // the GEMM of block i: with pageable host memory the calling thread stages them through the pinned ring while
+  // that GEMM runs.  Each GEMM keeps >= ~7 waves of 128x64 tiles so that the per-launch tail stays around 1 %.
   cudaStream_t sh = cx->h2d, sd = cx->d2h;
   const int RC = (!oa && m >= 8192) ? 2 : 1;
   const int64_t rstep = RC == 1 ? m : ((m + RC - 1) / RC + 127) / 128 * 128;
   const int64_t step = ((n + chunks - 1) / chunks + 63) / 64 * 64;
   constexpr int MAXB = 2 * 8;
-  cudaEvent_t ev_in[MAXB], ev_done[MAXB], ev_start;
-  LLA_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-  for (int j = 0; j < RC * chunks; j++) {
-    LLA_CUDA(cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming));
-    LLA_CUDA(cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming));
-  }
-  LLA_CUDA(cudaEventRecord(ev_start, st));
-  LLA_CUDA(cudaStreamWaitEvent(sh, ev_start, 0));
-  LLA_CUDA(cudaStreamWaitEvent(sd, ev_start, 0));
-  for (int r = 0; r < RC; r++) {
-    const int64_t r0 = (int64_t)r * rstep, r1 = (r0 + rstep < m) ? r0 + rstep : m;
-    if (RC == 1) LLA_TRY(stage_upload(sa, a, lda, sh));
-    else LLA_TRY(stage_upload_block(sa, a, lda, r0, r1, 0, k, sh));
-    for (int j = 0; j < chunks; j++) {
-      const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
-      if (c0 < n) {
-        if (r == 0) LLA_TRY(stage_upload_cols(sb, b, ldb, c0, c1, sh));
-        if (beta != 0.0) LLA_TRY(stage_upload_block(sc, c, ldc, r0, r1, c0, c1, sh));
-      }
-      LLA_CUDA(cudaEventRecord(ev_in[r * chunks + j], sh));
+  struct Events {
+    cudaEvent_t in[MAXB] = {}, done[MAXB] = {}, start = nullptr;
+    ~Events() {
+      for (auto e : in) if (e) cudaEventDestroy(e);
+      for (auto e : done) if (e) cudaEventDestroy(e);
+      if (start) cudaEventDestroy(start);
     }
+  } ev;
+  const int nblk = RC * chunks;
+  LLA_CUDA(cudaEventCreateWithFlags(&ev.start, cudaEventDisableTiming));
+  for (int j = 0; j < nblk; j++) {
+    LLA_CUDA(cudaEventCreateWithFlags(&ev.in[j], cudaEventDisableTiming));
+    LLA_CUDA(cudaEventCreateWithFlags(&ev.done[j], cudaEventDisableTiming));
   }
+  LLA_CUDA(cudaEventRecord(ev.start, st));
+  LLA_CUDA(cudaStreamWaitEvent(sh, ev.start, 0));
+  LLA_CUDA(cudaStreamWaitEvent(sd, ev.start, 0));
+  auto rows_of = [&](int r, int64_t& r0, int64_t& r1) { r0 = (int64_t)r * rstep; r1 = (r0 + rstep < m) ? r0 + rstep : m; };
+  auto cols_of = [&](int j, int64_t& c0, int64_t& c1) { c0 = (int64_t)j * step; c1 = (c0 + step < n) ? c0 + step : n; };
+  auto fetch = [&](int idx) -> int {   // operands that block idx needs and no earlier block has brought
+    const int r = idx / chunks, j = idx % chunks;
+    int64_t r0, r1, c0, c1;
+    rows_of(r, r0, r1); cols_of(j, c0, c1);
+    if (j == 0 && r0 < m) {
+      if (RC == 1) LLA_TRY(stage_upload(sa, a, lda, sh));
+      else LLA_TRY(stage_upload_block(sa, a, lda, r0, r1, 0, k, sh));
+    }
+    if (c0 < n && r0 < m) {
+      if (r == 0) LLA_TRY(stage_upload_cols(sb, b, ldb, c0, c1, sh));
+      if (beta != 0.0) LLA_TRY(stage_upload_block(sc, c, ldc, r0, r1, c0, c1, sh));
+    }
+    LLA_CUDA(cudaEventRecord(ev.in[idx], sh));
+    return 0;
+  };
+  LLA_TRY(fetch(0));
   tm.mark(1);
-  for (int r = 0; r < RC; r++) {
-    const int64_t r0 = (int64_t)r * rstep, r1 = (r0 + rstep < m) ? r0 + rstep : m;
-    if (r0 >= m) break;
-    for (int j = 0; j < chunks; j++) {
-      const int64_t c0 = (int64_t)j * step, c1 = (c0 + step < n) ? c0 + step : n;
-      if (c0 >= n) break;
-      LLA_CUDA(cudaStreamWaitEvent(st, ev_in[r * chunks + j], 0));
+  for (int idx = 0; idx < nblk; idx++) {
+    const int r = idx / chunks, j = idx % chunks;
+    int64_t r0, r1, c0, c1;
+    rows_of(r, r0, r1); cols_of(j, c0, c1);
+    const bool live = r0 < m && c0 < n;
+    if (live) {
+      LLA_CUDA(cudaStreamWaitEvent(st, ev.in[idx], 0));
       LLA_TRY(dgemm_dev(oa, ob, r1 - r0, c1 - c0, k, alpha, sa.ptr<double>() + r0, sa.ld, sb.ptr<double>() + c0 * sb.ld, sb.ld,
                         beta, sc.ptr<double>() + r0 + c0 * sc.ld, sc.ld, TRI_FULL, st));
-      LLA_CUDA(cudaEventRecord(ev_done[r * chunks + j], st));
-      LLA_CUDA(cudaStreamWaitEvent(sd, ev_done[r * chunks + j], 0));
+      LLA_CUDA(cudaEventRecord(ev.done[idx], st));
+    }
+    if (idx + 1 < nblk) LLA_TRY(fetch(idx + 1));
+    if (live) {
+      LLA_CUDA(cudaStreamWaitEvent(sd, ev.done[idx], 0));
       LLA_TRY(stage_download_block(sc, c, ldc, r0, r1, c0, c1, sd));
     }
   }
   tm.mark(2);
-  LLA_CUDA(cudaEventRecord(ev_start, sd));
-  LLA_CUDA(cudaStreamWaitEvent(st, ev_start, 0));
+  LLA_CUDA(cudaEventRecord(ev.start, sd));
+  LLA_CUDA(cudaStreamWaitEvent(st, ev.start, 0));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   LLA_CUDA(cudaStreamSynchronize(sd));
   tm.finish();
-  cudaEventDestroy(ev_start);
-  for (int j = 0; j < RC * chunks; j++) { cudaEventDestroy(ev_in[j]); cudaEventDestroy(ev_done[j]); }
   return 0;
 }
 
@@ -148,8 +162,9 @@ LLA_EXPORT void dgemm_(const char* transa, const char* transb, const fint* m_, c
   else if (ldb < (nrowb > 1 ? nrowb : 1)) bad = 10;
   else if (ldc < (m > 1 ? m : 1)) bad = 13;
   if (bad) { blas_arg_error("DGEMM ", bad); return; }
+  llacuda_clear_error();
   int r = dgemm_host(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc);
-  if (r != 0) fprintf(stderr, " ** llacuda: dgemm_ failed: %s\n", llacuda_last_error());
+  if (r != 0) blas_failure("dgemm_", r, c, ldc, m, n, sizeof(double));
 }
 
 LLA_EXPORT void llacuda_dgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
@@ -182,8 +197,9 @@ struct IntIn {
 };
 
 // Finished block rows of a factor go back to the caller while the factorisation is still running
-// (RowsFinalHook of the blocked drivers).  Only for page-locked host memory: a D2H copy into pageable
-// memory blocks the calling thread, which would stall the kernel queue of the following steps.
+// (RowsFinalHook of the blocked drivers).  Page-locked callers: asynchronous copies on the d2h stream.  Pageable
+// callers (LLA): the pinned ring's downloader thread (hostpipe.cu) drains them, so the calling thread keeps
+// queueing the following block steps.
 struct RowSender {
   const Staged* s;
   double* host;
@@ -196,7 +212,6 @@ struct RowSender {
   bool armed = false;
   int arm(const Staged& st, double* h, int64_t ld, cudaStream_t d2h, bool diag) {
     s = &st; host = h; ldh = ld; sd = d2h; from_diagonal = diag;
-    if (!host_is_pinned(h)) return 0;
     for (auto& e : ev) LLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     hook.fn = &RowSender::rows_final; hook.user = this;
     set_rows_final_hook(&hook);
@@ -259,7 +274,7 @@ static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, fint* ipiv,
   if (mn > 0) LLA_CUDA(cudaMemcpyAsync(pivots.host32(), piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
   LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   pivots.finish(); inf_out.finish();
   tm.finish();
   return 0;
@@ -275,7 +290,7 @@ LLA_EXPORT void dgetrf_(const fint* m_, const fint* n_, double* a, const fint* l
   if (lda < max1(m)) { *info = -4; return; }
   if (m == 0 || n == 0) return;
   int rc = dgetrf_host(m, n, a, lda, ipiv, info);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t lda, const fint* ipiv, double* b,
@@ -299,7 +314,7 @@ static int dgetrs_host(int op, int64_t n, int64_t nrhs, const double* a, int64_t
   tm.mark(2);
   LLA_TRY(stage_download(sb, b, ldb, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -318,7 +333,7 @@ LLA_EXPORT void dgetrs_(const char* trans, const fint* n_, const fint* nrhs_, co
   if (ldb < max1(n)) { *info = -8; return; }
   if (n == 0 || nrhs == 0) return;
   int rc = dgetrs_host(op, n, nrhs, a, lda, ipiv, b, ldb);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ipiv, double* b, int64_t ldb,
@@ -353,7 +368,7 @@ static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ipi
   LLA_CUDA(cudaMemcpyAsync(pivots.host32(), piv.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   pivots.finish(); inf_out.finish();
   tm.finish();
   return 0;
@@ -371,7 +386,7 @@ LLA_EXPORT void dgesv_(const fint* n_, const fint* nrhs_, double* a, const fint*
   if (ldb < max1(n)) { *info = -7; return; }
   if (n == 0) return;
   int rc = dgesv_host(n, nrhs, a, lda, ipiv, b, ldb, info);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, fint* info) {
@@ -399,7 +414,7 @@ static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, fint* info
   IntOut inf_out(info, 1);
   LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   inf_out.finish();
   tm.finish();
   return 0;
@@ -417,7 +432,7 @@ LLA_EXPORT void dpotrf_(const char* uplo, const fint* n_, double* a, const fint*
   if (lda < max1(n)) { *info = -4; return; }
   if (n == 0) return;
   int rc = dpotrf_host(upper, n, a, lda, info);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 static int dpotrs_host(bool upper, int64_t n, int64_t nrhs, const double* a, int64_t lda, double* b, int64_t ldb) {
@@ -436,7 +451,7 @@ static int dpotrs_host(bool upper, int64_t n, int64_t nrhs, const double* a, int
   tm.mark(2);
   LLA_TRY(stage_download(sb, b, ldb, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -456,7 +471,7 @@ LLA_EXPORT void dpotrs_(const char* uplo, const fint* n_, const fint* nrhs_, con
   if (ldb < max1(n)) { *info = -7; return; }
   if (n == 0 || nrhs == 0) return;
   int rc = dpotrs_host(upper, n, nrhs, a, lda, b, ldb);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 // llacuda_<name> aliases (INTEGRATION.md option B: re-pointed blas-lapack-function-name)
@@ -563,7 +578,7 @@ static int dsyrk_host(bool upper, int trans, int64_t n, int64_t k, double alpha,
   tm.mark(2);
   LLA_TRY(stage_download_tri(sc, c, ldc, upper, 0, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -584,8 +599,9 @@ LLA_EXPORT void dsyrk_(const char* uplo, const char* trans, const fint* n_, cons
   else if (lda < (nrowa > 1 ? nrowa : 1)) bad = 7;
   else if (ldc < (n > 1 ? n : 1)) bad = 10;
   if (bad) { blas_arg_error("DSYRK ", bad); return; }
+  llacuda_clear_error();
   int r = dsyrk_host(upper, op, n, k, *alpha, a, lda, *beta, c, ldc);
-  if (r != 0) fprintf(stderr, " ** llacuda: dsyrk_ failed: %s\n", llacuda_last_error());
+  if (r != 0) blas_failure("dsyrk_", r, c, ldc, n, n, sizeof(double));
 }
 
 LLA_EXPORT void llacuda_dsyrk(const char* uplo, const char* trans, const fint* n, const fint* k, const double* alpha,
@@ -613,7 +629,7 @@ static int dtrsm_host(bool left, bool upper, int op, bool unit, int64_t m, int64
   if (alpha != 1.0)  // B <- alpha B (the k = 0 path of the GEMM driver)
     LLA_TRY(dgemm_dev(0, 0, m, n, 0, 0.0, nullptr, 1, nullptr, 1, alpha, sb.ptr<double>(), sb.ld, TRI_FULL, st));
   Arena ar;
-  LLA_TRY(ar.reserve(tinv_bytes(na) + 1024));
+  LLA_TRY(ar.reserve(tinv_bytes(na) + 1024, st));
   double* tinv = (double*)ar.take(tinv_bytes(na));
   LLA_TRY(dtrtri_blocks_dev(upper, unit, na, sa.ptr<double>(), sa.ld, tinv, st));
   if (left) {
@@ -624,12 +640,12 @@ static int dtrsm_host(bool left, bool upper, int op, bool unit, int64_t m, int64
     LLA_TRY(dtranspose_dev(m, n, sb.ptr<double>(), sb.ld, st_t.ptr<double>(), st_t.ld, st));
     LLA_TRY(dtrsm_left_inv_dev(upper, op ? 0 : 1, n, m, sa.ptr<double>(), sa.ld, tinv, st_t.ptr<double>(), st_t.ld, st));
     LLA_TRY(dtranspose_dev(n, m, st_t.ptr<double>(), st_t.ld, sb.ptr<double>(), sb.ld, st));
-    LLA_CUDA(cudaStreamSynchronize(st));   // st_t goes back to the pool at the end of this scope
+    LLA_TRY(stage_sync(st));   // st_t goes back to the pool at the end of this scope
   }
   tm.mark(2);
   LLA_TRY(stage_download(sb, b, ldb, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -654,8 +670,9 @@ LLA_EXPORT void dtrsm_(const char* side, const char* uplo, const char* transa, c
   else if (lda < (nrowa > 1 ? nrowa : 1)) bad = 9;
   else if (ldb < (m > 1 ? m : 1)) bad = 11;
   if (bad) { blas_arg_error("DTRSM ", bad); return; }
+  llacuda_clear_error();
   int r = dtrsm_host(left, upper, op, unit, m, n, *alpha, a, lda, b, ldb);
-  if (r != 0) fprintf(stderr, " ** llacuda: dtrsm_ failed: %s\n", llacuda_last_error());
+  if (r != 0) blas_failure("dtrsm_", r, b, ldb, m, n, sizeof(double));
 }
 
 LLA_EXPORT void llacuda_dtrsm(const char* side, const char* uplo, const char* transa, const char* diag, const fint* m,
@@ -686,7 +703,7 @@ static int dposv_host(bool upper, int64_t n, int64_t nrhs, double* a, int64_t ld
   IntOut inf_out(info, 1);
   LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   inf_out.finish();
   tm.finish();
   return 0;
@@ -706,7 +723,7 @@ LLA_EXPORT void dposv_(const char* uplo, const fint* n_, const fint* nrhs_, doub
   if (ldb < max1(n)) { *info = -7; return; }
   if (n == 0 || nrhs == 0) { if (n == 0) return; }
   int rc = dposv_host(upper, n, nrhs, a, lda, b, ldb, info);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 LLA_EXPORT void llacuda_dposv(const char* uplo, const fint* n, const fint* nrhs, double* a, const fint* lda, double* b,
@@ -739,7 +756,7 @@ static int set_identity(Staged& s, int64_t n, cudaStream_t st) {
   LLA_CUDA(cudaMemset2DAsync(s.buf.p, (size_t)s.ld * 8, 0, (size_t)n * 8, (size_t)n, st));
   std::vector<double> ones((size_t)n, 1.0);   // pageable source: the copy is staged before the call returns
   LLA_CUDA(cudaMemcpy2DAsync(s.buf.p, (size_t)(s.ld + 1) * 8, ones.data(), 8, 8, (size_t)n, cudaMemcpyHostToDevice, st));
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   return 0;
 }
 
@@ -758,7 +775,7 @@ static int dgetri_host(int64_t n, double* a, int64_t lda, const fint* ipiv) {
   LLA_TRY(set_identity(sb, n, st));
   LLA_TRY(dgetrs_dev(0, n, n, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st));
   LLA_TRY(stage_download(sb, a, lda, st));
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   return 0;
 }
 
@@ -776,7 +793,7 @@ LLA_EXPORT void dgetri_(const fint* n_, double* a, const fint* lda_, const fint*
   for (int64_t i = 0; i < n; i++)
     if (a[i + i * lda] == 0.0) { *info = (fint)(i + 1); return; }   // U is exactly singular: nothing is computed
   int rc = dgetri_host(n, a, lda, ipiv);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 LLA_EXPORT void llacuda_dgetri(const fint* n, double* a, const fint* lda, const fint* ipiv, double* work, const fint* lwork,
                                fint* info) {
@@ -797,14 +814,14 @@ static int tri_inverse_host(bool potri, bool upper, bool unit, int64_t n, double
     LLA_TRY(dpotrs_dev(upper, n, n, sa.ptr<double>(), sa.ld, sb.ptr<double>(), sb.ld, st));
   } else {
     Arena ar;
-    LLA_TRY(ar.reserve(tinv_bytes(n) + 1024));
+    LLA_TRY(ar.reserve(tinv_bytes(n) + 1024, st));
     double* tinv = (double*)ar.take(tinv_bytes(n));
     LLA_TRY(dtrtri_blocks_dev(upper, unit, n, sa.ptr<double>(), sa.ld, tinv, st));
     LLA_TRY(dtrsm_left_inv_dev(upper, 0, n, n, sa.ptr<double>(), sa.ld, tinv, sb.ptr<double>(), sb.ld, st));
   }
   LLA_TRY(lacpy_tri(n, sb, sa, upper, !potri && unit, st));
   LLA_TRY(stage_download_tri(sa, a, lda, upper, 0, st));
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   return 0;
 }
 
@@ -821,7 +838,7 @@ LLA_EXPORT void dpotri_(const char* uplo, const fint* n_, double* a, const fint*
   for (int64_t i = 0; i < n; i++)
     if (a[i + i * lda] == 0.0) { *info = (fint)(i + 1); return; }
   int rc = tri_inverse_host(true, upper, false, n, a, lda);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 LLA_EXPORT void llacuda_dpotri(const char* uplo, const fint* n, double* a, const fint* lda, fint* info) {
   dpotri_(uplo, n, a, lda, info);
@@ -843,7 +860,7 @@ LLA_EXPORT void dtrtri_(const char* uplo, const char* diag, const fint* n_, doub
     for (int64_t i = 0; i < n; i++)
       if (a[i + i * lda] == 0.0) { *info = (fint)(i + 1); return; }
   int rc = tri_inverse_host(false, upper, unit, n, a, lda);
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 LLA_EXPORT void llacuda_dtrtri(const char* uplo, const char* diag, const fint* n, double* a, const fint* lda, fint* info) {
   dtrtri_(uplo, diag, n, a, lda, info);
@@ -894,12 +911,12 @@ LLA_EXPORT void llacuda_dgetrf_rm(const fint* m_, const fint* n_, double* a, con
     IntOut pivots(ipiv, mn), inf_out(info, 1);
     LLA_CUDA(cudaMemcpyAsync(pivots.host32(), piv.p, sizeof(int) * (size_t)mn, cudaMemcpyDeviceToHost, st));
     LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    LLA_CUDA(cudaStreamSynchronize(st));
+    LLA_TRY(stage_sync(st));
     pivots.finish(); inf_out.finish();
     return 0;
   };
   int rc = run();
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 /* solve on raw row-major arrays: reference src/linear-algebra.lisp:278-289; A is input-only there (&array-in), the
@@ -930,12 +947,12 @@ LLA_EXPORT void llacuda_dgesv_rm(const fint* n_, const fint* nrhs_, const double
     LLA_TRY(B.download(n, nrhs, b, ldb, st));   // untouched B comes back when INFO > 0 (the solve was skipped)
     IntOut inf_out(info, 1);
     LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    LLA_CUDA(cudaStreamSynchronize(st));
+    LLA_TRY(stage_sync(st));
     inf_out.finish();
     return 0;
   };
   int rc = run();
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 /* solve on an lu object: reference src/linear-algebra.lisp:264-276; LU (row-major, as LLA stores it) and ipiv are inputs */
@@ -962,11 +979,11 @@ LLA_EXPORT void llacuda_dgetrs_rm(const fint* n_, const fint* nrhs_, const doubl
     LLA_TRY(B.upload(n, nrhs, b, ldb, st));
     LLA_TRY(dgetrs_dev(0, n, nrhs, A.cm.ptr<double>(), A.cm.ld, (const int*)piv.p, B.cm.ptr<double>(), B.cm.ld, st));
     LLA_TRY(B.download(n, nrhs, b, ldb, st));
-    LLA_CUDA(cudaStreamSynchronize(st));
+    LLA_TRY(stage_sync(st));
     return 0;
   };
   int rc = run();
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 /* solve on a cholesky object: reference src/linear-algebra.lisp:291-301; the row-major lower factor is shared as it is
@@ -992,11 +1009,11 @@ LLA_EXPORT void llacuda_dpotrs_rm(const fint* n_, const fint* nrhs_, const doubl
     LLA_TRY(B.upload(n, nrhs, b, ldb, st));
     LLA_TRY(dpotrs_dev(true, n, nrhs, sa.ptr<double>(), sa.ld, B.cm.ptr<double>(), B.cm.ld, st));
     LLA_TRY(B.download(n, nrhs, b, ldb, st));
-    LLA_CUDA(cudaStreamSynchronize(st));
+    LLA_TRY(stage_sync(st));
     return 0;
   };
   int rc = run();
-  if (rc != 0) *info = rc;
+  if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
 
 // ------------------------------------------------------------------ ZGEMM
@@ -1028,7 +1045,7 @@ static int zgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuDoubleC
   tm.mark(2);
   LLA_TRY(stage_download(sc, c, ldc, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -1051,9 +1068,10 @@ LLA_EXPORT void zgemm_(const char* transa, const char* transb, const fint* m_, c
   else if (ldb < (nrowb > 1 ? nrowb : 1)) bad = 10;
   else if (ldc < (m > 1 ? m : 1)) bad = 13;
   if (bad) { blas_arg_error("ZGEMM ", bad); return; }
+  llacuda_clear_error();
   int r = zgemm_host(oa, ob, m, n, k, *(const cuDoubleComplex*)alpha, (const cuDoubleComplex*)a, lda,
                      (const cuDoubleComplex*)b, ldb, *(const cuDoubleComplex*)beta, (cuDoubleComplex*)c, ldc);
-  if (r != 0) fprintf(stderr, " ** llacuda: zgemm_ failed: %s\n", llacuda_last_error());
+  if (r != 0) blas_failure("zgemm_", r, c, ldc, m, n, sizeof(cuDoubleComplex));
 }
 LLA_EXPORT void llacuda_zgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
                               const void* alpha, const void* a, const fint* lda, const void* b, const fint* ldb,
@@ -1100,7 +1118,7 @@ static int sgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, float alp
   tm.mark(2);
   LLA_TRY(stage_download(sc, c, ldc, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -1123,8 +1141,9 @@ LLA_EXPORT void sgemm_(const char* transa, const char* transb, const fint* m_, c
   else if (ldb < (nrowb > 1 ? nrowb : 1)) bad = 10;
   else if (ldc < (m > 1 ? m : 1)) bad = 13;
   if (bad) { blas_arg_error("SGEMM ", bad); return; }
+  llacuda_clear_error();
   int r = sgemm_host(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc);
-  if (r != 0) fprintf(stderr, " ** llacuda: sgemm_ failed: %s\n", llacuda_last_error());
+  if (r != 0) blas_failure("sgemm_", r, c, ldc, m, n, sizeof(float));
 }
 LLA_EXPORT void llacuda_sgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,
                               const float* alpha, const float* a, const fint* lda, const float* b, const fint* ldb,

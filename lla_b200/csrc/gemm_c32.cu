@@ -137,7 +137,7 @@ static int cgemm_host(int oa, int ob, int64_t m, int64_t n, int64_t k, cuFloatCo
   tm.mark(2);
   LLA_TRY(stage_download(sc, c, ldc, st));
   tm.mark(3);
-  LLA_CUDA(cudaStreamSynchronize(st));
+  LLA_TRY(stage_sync(st));
   tm.finish();
   return 0;
 }
@@ -166,9 +166,10 @@ extern "C" void cgemm_(const char* transa, const char* transb, const fint* m_, c
     fprintf(stderr, " ** llacuda: %s\n", msg);
     return;
   }
+  llacuda_clear_error();
   int r = cgemm_host(oa, ob, m, n, k, *(const cuFloatComplex*)alpha, (const cuFloatComplex*)a, lda,
                      (const cuFloatComplex*)b, ldb, *(const cuFloatComplex*)beta, (cuFloatComplex*)c, ldc);
-  if (r != 0) fprintf(stderr, " ** llacuda: cgemm_ failed: %s\n", llacuda_last_error());
+  if (r != 0) blas_failure("cgemm_", r, c, ldc, m, n, sizeof(cuFloatComplex));
 }
 
 extern "C" void llacuda_cgemm(const char* transa, const char* transb, const fint* m, const fint* n, const fint* k,

@@ -328,10 +328,9 @@ int sgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, float alpha, co
   p.M = (int)m; p.N = (int)n; p.K = (int)k; p.C = C; p.ldc = ldc; p.alpha = alpha; p.beta = beta;
   p.a_mn_major = ta ? 0 : 1;
   p.b_mn_major = tb ? 1 : 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     LLA_CUDA(cudaFuncSetAttribute(lla_sgemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg::SMEM_BYTES));
-    configured = true;
   }
   dim3 grid((unsigned)((m + sg::BM - 1) / sg::BM), (unsigned)((n + sg::BN - 1) / sg::BN));
   lla_sgemm_tcgen05_kernel<<<grid, sg::NUM_THREADS, sg::SMEM_BYTES, st>>>(tmA, tmB, p);

@@ -277,10 +277,9 @@ static int launch_cfg(const DgemmParams& p, cudaStream_t st, int64_t max_ctas = 
   using TSB = TileShape<BN, BK, TB>;
   constexpr size_t SMEM = size_t(STAGES) * (TSA::ELEMS + TSB::ELEMS) * sizeof(double);
   auto kern = lla_dgemm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB, AL16, MINB>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     LLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
   }
   int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   if (max_ctas > 0 && tiles > max_ctas) tiles = max_ctas;

@@ -186,10 +186,9 @@ static int zlaunch(const ZgemmParams& p, cudaStream_t st) {
   using TSB = ZTile<BN, BK, TB>;
   constexpr size_t SMEM = size_t(STAGES) * (TSA::ELEMS + TSB::ELEMS) * sizeof(double2);
   auto kern = lla_zgemm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     LLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
   }
   int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   kern<<<(unsigned)tiles, NT, SMEM, st>>>(p);

@@ -22,6 +22,10 @@ namespace llacuda {
 void set_error(const char* file, int line, const char* what, int code);
 int  record_cuda_error(cudaError_t e, const char* file, int line);
 
+// A BLAS-style entry point (void, no INFO) failed on the device side: drain the streams, call the installed handler,
+// then stop like XERBLA (default) or -- error mode 1 -- poison the rows x cols output with NaN and return.
+void blas_failure(const char* routine, int rc, void* out, int64_t ld, int64_t rows, int64_t cols, size_t es);
+
 #define LLA_CUDA(call)                                                        \
   do {                                                                        \
     cudaError_t _e = (call);                                                  \
@@ -43,6 +47,9 @@ struct ApiLock {
 };
 
 // ------------------------------------------------------------------ context
+constexpr int MAX_DEV = 16;
+int cur_dev();                        // cudaGetDevice of the calling thread (-1 without a device)
+
 struct Context {
   int device = -1;
   int sm_count = 0;
@@ -51,31 +58,43 @@ struct Context {
   cudaStream_t h2d = nullptr;        // staging streams
   cudaStream_t d2h = nullptr;
   cudaEvent_t ev[8] = {};
-  // grow-only device workspace (factorisation scratch: pivots, info, barrier words, T inverses)
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
-  // pinned staging ring for pageable host operands
-  void* pin[4] = {};
-  size_t pin_bytes = 0;
+  cudaStream_t own_stream = nullptr; // the library's stream while a caller-owned one is adopted (llacuda_set_stream)
   // timing of the last host-pointer call (ms): [0]=h2d [1]=compute [2]=d2h [3]=total
   float last_ms[4] = {};
 };
-Context* ctx();                       // lazily initialised, per process, current device
-int ensure_workspace(size_t bytes);   // ctx()->ws valid for >= bytes afterwards
+// Lazily initialised, one per device: the context of the calling thread's current device.  The classic entry
+// points run on whatever device is current when they are first called (llacuda_set_device); the multi-GPU engine
+// (dist.cu) drives one thread per device, each of which sees its own context here.
+Context* ctx();
 
-// Bump allocator over ctx()->ws for the scratch of ONE top-level call: reserve() once with the
-// total (may grow the arena: synchronises), then take() pieces (256-byte aligned).
+// Scratch that belongs to one stream (grow-only, zero-filled when it is (re)allocated): every user is work queued on
+// that stream, so successive calls may alias it without any event.  Scratch of different streams never aliases,
+// which is what lets a panel be factored on one stream while another stream solves or updates.
+void* stream_scratch(cudaStream_t st, size_t bytes);
+
+// Bump allocator over the scratch of ONE stream for ONE top-level call: reserve() once with the total (may grow the
+// stream's scratch: synchronises that stream), then take() pieces (256-byte aligned).
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, used = 0;
-  int reserve(size_t bytes);
+  int reserve(size_t bytes, cudaStream_t st);
   void* take(size_t bytes);
 };
 
-// Scratch that belongs to one stream (grow-only): for device entry points that may run concurrently with a
-// factorisation on another stream (the block-cyclic drivers of lla_b200/dist.py update on one stream while the
-// next panel is factored on a second one), where the shared per-call arena above must not be touched.
-void* stream_scratch(cudaStream_t st, size_t bytes);
+// cudaFuncSetAttribute is per device: `static DeviceOnce once; if (once.first()) { ...set attributes... }`
+struct DeviceOnce {
+  bool done[MAX_DEV] = {};
+  bool first() {
+    int d = cur_dev();
+    if (d < 0 || d >= MAX_DEV || done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
+// synchronise every stream of the current device's context (error paths of the host-pointer entry points: nothing
+// may still read or write the caller's buffers, or the pooled device blocks, after the call has returned)
+void drain_streams();
 
 // number of llacuda kernels launched by this process (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);

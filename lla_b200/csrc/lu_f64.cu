@@ -21,6 +21,7 @@
 #include "../../include/llacuda.h"
 
 #include <cooperative_groups.h>
+#include <atomic>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -452,10 +453,9 @@ int dlaswp_skip_dev(int64_t ncols, int64_t skip0, int64_t skip1, double* A, int6
   if (eff <= 0 || k2 <= k1) return 0;
   static const bool no_dense = getenv("LLACUDA_LASWP_OLD") != nullptr;
   if (k2 - k1 > 2 * SW_CHUNK && k2 - k1 <= LS_R && !no_dense) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
       LLA_CUDA(cudaFuncSetAttribute(lla_dlaswp_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
-      configured = true;
     }
     unsigned g = (unsigned)((eff + LS_CB - 1) / LS_CB);
     lla_dlaswp_dense_kernel<<<g, LS_T, LS_SMEM, st>>>(A, lda, ncols, skip0, skip1, k1, k2, ipiv, forward, abort_flag);
@@ -489,7 +489,7 @@ struct LuCtx {
   cudaStream_t st;
 };
 
-static unsigned g_panel_epoch = 1;
+static std::atomic<unsigned> g_panel_epoch{1};
 
 static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   // panel = A[j0 : j0+m, j0 : j0+w]
@@ -502,8 +502,8 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   PanelHdr* h_ = L.hdrs;
   PanelRow* r_ = L.rows;
   PanelRow* rj_ = L.rowj;
-  unsigned epoch = g_panel_epoch++ & 0x03ffffffu;
-  if (epoch == 0) epoch = g_panel_epoch++ & 0x03ffffffu;
+  unsigned epoch = g_panel_epoch.fetch_add(1) & 0x03ffffffu;
+  if (epoch == 0) epoch = g_panel_epoch.fetch_add(1) & 0x03ffffffu;
   // LLACUDA_PANEL_DBG=1: per-column phase breakdown of the exchange (instrumented instantiation of the kernel)
   static unsigned long long* dbg = nullptr;
   static bool dbg_checked = false;
@@ -511,7 +511,7 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
     dbg_checked = true;
     if (getenv("LLACUDA_PANEL_DBG")) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
   }
-  if (dbg && (g_panel_epoch % 128) == 0) {
+  if (dbg && (g_panel_epoch.load() % 128) == 0) {
     unsigned long long h[16];
     cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
     if (h[6]) fprintf(stderr, "panel phases, cycles/column over %llu columns (m=%lld): apply+cand=%llu publish=%llu own-update=%llu poll=%llu fetch=%llu sync=%llu\n",
@@ -657,7 +657,8 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   if (m <= 0 || n <= 0) return 0;
   int maxG = (int)((m + PR - 1) / PR);
   // co-residency bound of the cooperative panel kernel
-  static int per_sm = 0;
+  static int per_sm_dev[MAX_DEV] = {};
+  int& per_sm = per_sm_dev[c->device];
   if (per_sm == 0) {
     LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
@@ -669,7 +670,7 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   }
   const int64_t mn = m < n ? m : n;
   Arena ar;
-  LLA_TRY(ar.reserve(sizeof(PanelHdr) * 2 * maxG + sizeof(PanelRow) * (2 * maxG + 2) + tinv_bytes(mn) + 4096));
+  LLA_TRY(ar.reserve(sizeof(PanelHdr) * 2 * maxG + sizeof(PanelRow) * (2 * maxG + 2) + tinv_bytes(mn) + 4096, st));
   LuCtx L;
   L.A = A; L.lda = lda; L.M = m; L.N = n; L.ipiv = ipiv; L.info = info_dev; L.st = st;
   L.swap_c0 = 0; L.swap_c1 = n;
@@ -686,7 +687,7 @@ int dgetrs_dev(int op, int64_t n, int64_t nrhs, const double* A, int64_t lda, co
   // inverses of the 128 x 128 diagonal blocks of L and of U (two batched launches); both
   // triangular solves are then GEMMs only
   Arena ar;
-  LLA_TRY(ar.reserve(2 * tinv_bytes(n) + 1024));
+  LLA_TRY(ar.reserve(2 * tinv_bytes(n) + 1024, st));
   double* linv = (double*)ar.take(tinv_bytes(n));
   double* uinv = (double*)ar.take(tinv_bytes(n));
   LLA_TRY(dtrtri_blocks_dev(false, true, n, A, lda, linv, st, abort_flag));

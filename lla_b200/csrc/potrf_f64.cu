@@ -155,13 +155,12 @@ int dpotrf_dev(bool upper, int64_t n, double* A, int64_t lda, int* info_dev, cud
   if (!ctx()) return LLACUDA_ERR_NO_DEVICE;
   LLA_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
   if (n <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     LLA_CUDA(cudaFuncSetAttribute(lla_dpotrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T128_SMEM));
-    configured = true;
   }
   Arena ar;
-  LLA_TRY(ar.reserve(tinv_bytes(n)));
+  LLA_TRY(ar.reserve(tinv_bytes(n), st));
   double* uinv = (double*)ar.take(tinv_bytes(n));
   if (!upper) LLA_TRY(dtranspose_inplace_dev(n, A, lda, st));
   LLA_TRY(potrf_blocked(n, A, lda, uinv, info_dev, st));
@@ -175,7 +174,7 @@ int dpotrs_dev(bool upper, int64_t n, int64_t nrhs, const double* A, int64_t lda
   // inverses of the 128 x 128 diagonal blocks of the factor (one batched launch), then both
   // triangular solves are GEMMs only
   Arena ar;
-  LLA_TRY(ar.reserve(tinv_bytes(n)));
+  LLA_TRY(ar.reserve(tinv_bytes(n), st));
   double* tinv = (double*)ar.take(tinv_bytes(n));
   LLA_TRY(dtrtri_blocks_dev(upper, false, n, A, lda, tinv, st, abort_flag));
   if (upper) {  // A = U^T U :  U^T y = b ; U x = y

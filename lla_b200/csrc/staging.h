@@ -40,6 +40,9 @@ int stage_download_tri(const Staged& s, void* host, int64_t ldh, bool upper, int
 // rows [r0, r1) of the columns [c0, cols)
 int stage_download_rows(const Staged& s, void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, cudaStream_t st);
 bool host_is_pinned(const void* p);
+// end of a host-pointer call: completes the pageable transfers this thread started through the pinned ring
+// (hostpipe.cu), then synchronises `st`
+int stage_sync(cudaStream_t st);
 // column range [c0, c1) only
 int stage_upload_cols(Staged& s, const void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st);
 int stage_download_cols(const Staged& s, void* host, int64_t ldh, int64_t c0, int64_t c1, cudaStream_t st);

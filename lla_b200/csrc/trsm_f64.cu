@@ -144,10 +144,9 @@ __global__ void __launch_bounds__(T128_THREADS) lla_dtrtri_blocks_kernel(int64_t
 int dtrtri_blocks_dev(bool upper, bool unit, int64_t m, const double* T, int64_t ldt, double* Tinv, cudaStream_t st,
                       const int* abort_flag) {
   if (m <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     LLA_CUDA(cudaFuncSetAttribute(lla_dtrtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T128_SMEM));
-    configured = true;
   }
   unsigned grid = (unsigned)((m + IB - 1) / IB);
   lla_dtrtri_blocks_kernel<<<grid, T128_THREADS, T128_SMEM, st>>>(m, T, ldt, Tinv, upper, unit, abort_flag);
