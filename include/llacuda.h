@@ -38,6 +38,7 @@ extern "C" {
 #define LLACUDA_ERR_NO_DEVICE (-10001)
 #define LLACUDA_ERR_CUDA_BASE (-20000) /* info = BASE - cudaError_t */
 #define LLACUDA_ERR_BAD_ARG   (-10002)
+#define LLACUDA_ERR_NCCL_BASE (-30000) /* info = BASE - ncclResult_t (multi-GPU entry points) */
 
 /* ------------------------------------------------------------------ runtime / helpers */
 int  llacuda_set_device(int device);           /* before the first call; one device per process */
@@ -228,6 +229,64 @@ void llacuda_dgetrs_rm(const llacuda_int* n, const llacuda_int* nrhs, const doub
                        const llacuda_int* ipiv, double* b, const llacuda_int* ldb, llacuda_int* info);
 void llacuda_dpotrs_rm(const llacuda_int* n, const llacuda_int* nrhs, const double* l, const llacuda_int* lda, double* b,
                        const llacuda_int* ldb, llacuda_int* info);
+
+/* ------------------------------------------------------------------ group 4: one problem over the GPUs of one box
+ * BASELINE.json north_star: "Large GEMM and blocked LU/Cholesky are partitioned across one 8xB200 box as a 2D block-cyclic
+ * layout, broadcasting panels with NCCL over NVLink; batched small solves shard one batch slice per GPU ... The Lisp API
+ * stays unchanged".  LLA issues one synchronous foreign-funcall from one process (reference src/fortran-call.lisp:428-439),
+ * so the engine runs in that process: ncclCommInitAll over the visible devices, one host thread per GPU.
+ *
+ *   llacuda_dist_init_all(ndev, P, Q)   ndev <= 0: every visible GPU; P, Q <= 0: most-square grid.  Or set LLACUDA_GPUS=N
+ *                                       and the plain Fortran symbols (dgemm_, dgesv_, dgetrf_, dpotrf_, zgemm_) route
+ *                                       problems of order >= LLACUDA_DIST_MIN_N (8192) here by themselves.
+ *   llacuda_pdgemm ... llacuda_pdgesv   HOST pointers, the argument lists of dgemm_ / dpotrf_ / dposv_ / dpotrs_ /
+ *                                       dgetrf_ / dgesv_ / zgemm_ (same INFO and failure conventions).  Grids: GEMM most
+ *                                       square, factorisations block columns (1 x N) unless LLACUDA_LU_GRID /
+ *                                       LLACUDA_CHOL_GRID / LLACUDA_GEMM_GRID = "PxQ" say otherwise; block size 512.
+ *   llacuda_dist_init_rank + *_local    the same rank functions with one rank per PROCESS on block-cyclic operands that
+ *                                       already live in HBM (bench.py --gpus N, tests): local part of an Np x Np matrix
+ *                                       = column-major Np/P x Np/Q, local block (li, lj) = global block (li P + p, lj Q + q),
+ *                                       rank = p Q + q, Np a multiple of nb lcm(P, Q). */
+int  llacuda_dist_init_all(int ndev, int P, int Q);
+int  llacuda_dist_unique_id(void* id128);                 /* 128 bytes; rank 0 creates, the launcher distributes */
+int  llacuda_dist_init_rank(int nranks, int rank, const void* id128, int P, int Q);   /* on the current device */
+int  llacuda_dist_set_grid(int P, int Q);                 /* collective over the ranks */
+int  llacuda_dist_info(int* nranks, int* P, int* Q, int* single_process, int* rank);
+int  llacuda_dist_nccl_version(void);
+int  llacuda_dist_finalize(void);
+void* llacuda_dist_stream(void);                          /* launcher mode: the stream the rank functions end on */
+void llacuda_pdgemm(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+                    const double* alpha, const double* a, const llacuda_int* lda, const double* b, const llacuda_int* ldb,
+                    const double* beta, double* c, const llacuda_int* ldc);
+void llacuda_pzgemm(const char* transa, const char* transb, const llacuda_int* m, const llacuda_int* n, const llacuda_int* k,
+                    const void* alpha, const void* a, const llacuda_int* lda, const void* b, const llacuda_int* ldb,
+                    const void* beta, void* c, const llacuda_int* ldc);
+void llacuda_pdpotrf(const char* uplo, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_pdposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda, double* b,
+                    const llacuda_int* ldb, llacuda_int* info);
+void llacuda_pdpotrs(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const double* a, const llacuda_int* lda,
+                     double* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_pdgetrf(const llacuda_int* m, const llacuda_int* n, double* a, const llacuda_int* lda, llacuda_int* ipiv,
+                     llacuda_int* info);
+void llacuda_pdgesv(const llacuda_int* n, const llacuda_int* nrhs, double* a, const llacuda_int* lda, llacuda_int* ipiv, double* b,
+                    const llacuda_int* ldb, llacuda_int* info);
+/* BASELINE configs[3]: batch of n x n systems (n <= 32, nrhs <= 8), contiguous [batch][n][n] / [batch][nrhs][n]
+ * column-major images on the HOST; one contiguous batch slice per GPU, no collective; ipiv / info int32, may be NULL */
+int  llacuda_pdgesv_batched(int n, int nrhs, int64_t batch, double* a, double* b, int* ipiv, int* info, int keep_lu);
+int  llacuda_pdgemm_local(int64_t Mp, int64_t Np, int64_t Kp, int64_t nb, double alpha, const double* A, int64_t lda,
+                          const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+int  llacuda_pzgemm_local(int64_t Mp, int64_t Np, int64_t Kp, int64_t nb, const double* alpha2, const void* A, int64_t lda,
+                          const void* B, int64_t ldb, const double* beta2, void* C, int64_t ldc);
+int  llacuda_pdpotrf_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* info);            /* info: host int */
+int  llacuda_pdgetrf_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv_dev, int* info);
+int  llacuda_pdgetrs_local(int64_t Np, int64_t nb, const double* LU, int64_t lld, const int* ipiv_dev, double* B, int64_t ldb,
+                           int64_t nrhs);                                                         /* B replicated */
+int  llacuda_pdpotrs_local(int64_t Np, int64_t nb, const double* U, int64_t lld, double* B, int64_t ldb, int64_t nrhs);
+/* ownership arithmetic of the layout (pure functions) */
+int64_t llacuda_dist_numroc(int64_t n, int64_t nb, int iproc, int nprocs);
+int64_t llacuda_dist_padded(int64_t n, int64_t nb, int P, int Q);
+int64_t llacuda_dist_l2g(int64_t l, int64_t nb, int iproc, int nprocs);
+void llacuda_dist_default_grid(int world, int* P, int* Q);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,364 @@
+// lla_b200/csrc/dist.cu -- the multi-GPU engine: NCCL binding, process grid, rank threads (see dist.h).
+//
+// The reference has no multi-device code; this is the partitioning BASELINE.json's north_star
+// asks for, behind the same kind of C entry points LLA's foreign-funcall can reach (include/llacuda.h, group 4).
+#include "dist.h"
+#include "../../include/llacuda.h"
+
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace llacuda {
+
+// ------------------------------------------------------------------ NCCL, bound at run time
+static NcclApi g_nccl;
+static bool g_nccl_ok = false, g_nccl_tried = false;
+static std::mutex g_nccl_mu;
+
+const NcclApi* nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl_tried) return g_nccl_ok ? &g_nccl : nullptr;
+  g_nccl_tried = true;
+  // a process that already carries NCCL (PyTorch) gets that copy back: same soname
+  void* h = nullptr;
+  if (const char* e = getenv("LLACUDA_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error(__FILE__, __LINE__, "libnccl.so.2 not found (needed only for the multi-GPU entry points)", -1);
+    return nullptr;
+  }
+  bool ok = true;
+  auto bind = [&](const char* name) -> void* {
+    void* p = dlsym(h, name);
+    if (!p) ok = false;
+    return p;
+  };
+#define B(field, sym) g_nccl.field = (decltype(g_nccl.field))bind(sym)
+  B(GetUniqueId, "ncclGetUniqueId");
+  B(CommInitRank, "ncclCommInitRank");
+  B(CommInitAll, "ncclCommInitAll");
+  B(CommSplit, "ncclCommSplit");
+  B(CommDestroy, "ncclCommDestroy");
+  B(Broadcast, "ncclBroadcast");
+  B(AllReduce, "ncclAllReduce");
+  B(AllGather, "ncclAllGather");
+  B(Send, "ncclSend");
+  B(Recv, "ncclRecv");
+  B(GroupStart, "ncclGroupStart");
+  B(GroupEnd, "ncclGroupEnd");
+  B(GetErrorString, "ncclGetErrorString");
+  B(GetVersion, "ncclGetVersion");
+#undef B
+  if (!ok) {
+    set_error(__FILE__, __LINE__, "libnccl.so.2 lacks a required symbol (need NCCL >= 2.18 for ncclCommSplit)", -1);
+    return nullptr;
+  }
+  g_nccl_ok = true;
+  return &g_nccl;
+}
+
+int record_nccl_error(ncclResult_t r, const char* file, int line) {
+  const NcclApi* n = g_nccl_ok ? &g_nccl : nullptr;
+  char msg[200];
+  snprintf(msg, sizeof(msg), "NCCL: %s", n ? n->GetErrorString(r) : "?");
+  set_error(file, line, msg, (int)r);
+  return LLACUDA_ERR_NCCL_BASE - (int)r;
+}
+
+int64_t lcm(int64_t a, int64_t b) {
+  int64_t x = a, y = b;
+  while (y) { int64_t t = x % y; x = y; y = t; }
+  return a / x * b;
+}
+
+// ------------------------------------------------------------------ engine state
+static Engine g_eng;
+static std::vector<Rank> g_ranks;
+static std::mutex g_eng_mu;
+
+// rank threads of the single-process mode: persistent, one per device, parked on a condition variable
+struct Crew {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  const std::function<int(Rank&)>* job = nullptr;
+  unsigned long long gen = 0;
+  int pending = 0;
+  std::vector<int> rc;
+  bool quit = false;
+};
+static Crew* g_crew = nullptr;
+
+static void crew_loop(int r) {
+  Rank& R = g_ranks[(size_t)r];
+  cudaSetDevice(R.dev);
+  unsigned long long seen = 0;
+  for (;;) {
+    const std::function<int(Rank&)>* job;
+    {
+      std::unique_lock<std::mutex> lk(g_crew->mu);
+      g_crew->cv_go.wait(lk, [&] { return g_crew->quit || g_crew->gen != seen; });
+      if (g_crew->quit) return;
+      seen = g_crew->gen;
+      job = g_crew->job;
+    }
+    llacuda_clear_error();
+    int rc = (*job)(R);
+    if (rc != 0) {
+      snprintf(R.err, sizeof(R.err), "rank %d (device %d): %s", R.rank, R.dev, llacuda_last_error());
+      R.err_code = rc;
+    }
+    {
+      std::lock_guard<std::mutex> lk(g_crew->mu);
+      g_crew->rc[(size_t)r] = rc;
+      if (--g_crew->pending == 0) g_crew->cv_done.notify_all();
+    }
+  }
+}
+
+const Engine& engine() { return g_eng; }
+
+int run_ranks(const std::function<int(Rank&)>& fn) {
+  if (!g_eng.ready) {
+    set_error(__FILE__, __LINE__, "multi-GPU engine not initialised (llacuda_dist_init_all / llacuda_dist_init_rank)", -1);
+    return LLACUDA_ERR_BAD_ARG;
+  }
+  if (!g_eng.single_process) {
+    Rank& R = g_ranks[0];
+    int dev = cur_dev();
+    if (dev != R.dev) cudaSetDevice(R.dev);
+    return fn(R);
+  }
+  int prev = cur_dev();
+  {
+    std::unique_lock<std::mutex> lk(g_crew->mu);
+    g_crew->job = &fn;
+    g_crew->pending = g_eng.nranks;
+    std::fill(g_crew->rc.begin(), g_crew->rc.end(), 0);
+    g_crew->gen++;
+    g_crew->cv_go.notify_all();
+    g_crew->cv_done.wait(lk, [&] { return g_crew->pending == 0; });
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  for (int r = 0; r < g_eng.nranks; r++)
+    if (g_crew->rc[(size_t)r] != 0) {
+      set_error(__FILE__, __LINE__, g_ranks[(size_t)r].err, g_ranks[(size_t)r].err_code);
+      return g_crew->rc[(size_t)r];
+    }
+  return 0;
+}
+
+static void choose_grid(int world, int* P, int* Q) {   // most square, P <= Q (8 GPUs: 2 x 4, as SURVEY.md section 8e plans)
+  int p = 1;
+  for (int c = 1; c * c <= world; c++)
+    if (world % c == 0) p = c;
+  *P = p;
+  *Q = world / p;
+}
+
+static int rank_resources(Rank& R) {
+  LLA_CUDA(cudaSetDevice(R.dev));
+  if (!ctx()) return LLACUDA_ERR_NO_DEVICE;
+  int lo = 0, hi = 0;
+  LLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  LLA_CUDA(cudaStreamCreateWithPriority(&R.main, cudaStreamNonBlocking, lo));
+  LLA_CUDA(cudaStreamCreateWithPriority(&R.side, cudaStreamNonBlocking, hi));
+  for (auto& e : R.ev) LLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  LLA_CUDA(cudaMalloc((void**)&R.dflag, 8 * sizeof(int)));
+  LLA_CUDA(cudaMemset(R.dflag, 0, 8 * sizeof(int)));
+  LLA_CUDA(cudaHostAlloc((void**)&R.hflag, 8 * sizeof(int), cudaHostAllocPortable));
+  return 0;
+}
+
+static int split_grid(Rank& R, int P, int Q) {
+  const NcclApi* n = nccl();
+  if (!n) return LLACUDA_ERR_BAD_ARG;
+  R.P = P; R.Q = Q;
+  R.p = R.rank / Q; R.q = R.rank % Q;
+  for (auto& g : R.grids)
+    if (g.P == P && g.Q == Q) { R.rowc = g.rowc; R.colc = g.colc; return 0; }
+  R.rowc = R.colc = nullptr;
+  // every rank takes part in both splits; a 1-wide dimension needs no communicator
+  if (Q > 1) LLA_NCCL(n->CommSplit(R.world, R.p, R.q, &R.rowc, nullptr));
+  if (P > 1) LLA_NCCL(n->CommSplit(R.world, R.q, R.p, &R.colc, nullptr));
+  R.grids.push_back({P, Q, R.rowc, R.colc});
+  return 0;
+}
+
+int regrid(int P, int Q) {
+  if (!g_eng.ready || P < 1 || Q < 1 || P * Q != g_eng.nranks) {
+    set_error(__FILE__, __LINE__, "regrid: P * Q must equal the number of ranks", P * Q);
+    return LLACUDA_ERR_BAD_ARG;
+  }
+  if (P == g_eng.P && Q == g_eng.Q) return 0;
+  int rc = run_ranks([&](Rank& R) { return split_grid(R, P, Q); });
+  if (rc == 0) { g_eng.P = P; g_eng.Q = Q; }
+  return rc;
+}
+
+int finish_info(Rank& R, int* info_out) {
+  const NcclApi* n = nccl();
+  // smallest positive INFO over the ranks (the first failing leading minor / zero pivot wins), 0 if none
+  extern void launch_info_encode(int* flag, bool decode, cudaStream_t st);
+  if (R.nranks > 1) {
+    launch_info_encode(R.dflag, false, R.main);
+    LLA_NCCL(n->AllReduce(R.dflag, R.dflag, 1, ncclInt32, ncclMin, R.world, R.main));
+    launch_info_encode(R.dflag, true, R.main);
+  }
+  LLA_CUDA(cudaMemcpyAsync(R.hflag, R.dflag, sizeof(int), cudaMemcpyDeviceToHost, R.main));
+  LLA_CUDA(cudaStreamSynchronize(R.main));
+  LLA_CUDA(cudaStreamSynchronize(R.side));
+  if (info_out) *info_out = R.hflag[0];
+  return 0;
+}
+
+}  // namespace llacuda
+
+using namespace llacuda;
+
+// ------------------------------------------------------------------ C ABI: engine life cycle
+extern "C" {
+
+int llacuda_dist_init_all(int ndev, int P, int Q) {
+  ApiLock api_lock;
+  std::lock_guard<std::mutex> lk(g_eng_mu);
+  if (g_eng.ready) {
+    if (g_eng.single_process && (ndev <= 0 || ndev == g_eng.nranks)) return (P > 0 && Q > 0) ? regrid(P, Q) : 0;
+    set_error(__FILE__, __LINE__, "llacuda_dist_init_all: engine already initialised with another shape", g_eng.nranks);
+    return LLACUDA_ERR_BAD_ARG;
+  }
+  const NcclApi* n = nccl();
+  if (!n) return LLACUDA_ERR_BAD_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    set_error(__FILE__, __LINE__, "no CUDA device: llacuda has no CPU fallback", -1);
+    return LLACUDA_ERR_NO_DEVICE;
+  }
+  if (ndev <= 0 || ndev > count) ndev = count;
+  if (ndev > MAX_DEV) ndev = MAX_DEV;
+  if (P <= 0 || Q <= 0 || P * Q != ndev) choose_grid(ndev, &P, &Q);
+  const int prev = cur_dev();
+  g_ranks.assign((size_t)ndev, Rank());
+  std::vector<ncclComm_t> comms((size_t)ndev);
+  std::vector<int> devs((size_t)ndev);
+  for (int r = 0; r < ndev; r++) devs[(size_t)r] = r;
+  LLA_NCCL(n->CommInitAll(comms.data(), ndev, devs.data()));
+  for (int r = 0; r < ndev; r++) {
+    Rank& R = g_ranks[(size_t)r];
+    R.rank = r; R.nranks = ndev; R.dev = r; R.world = comms[(size_t)r];
+    LLA_TRY(rank_resources(R));
+    for (int s = 0; s < ndev; s++)   // panels and operands also move by direct peer copies where that is cheaper
+      if (s != r) { int can = 0; cudaDeviceCanAccessPeer(&can, r, s); if (can) { cudaDeviceEnablePeerAccess(s, 0); cudaGetLastError(); } }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  g_crew = new Crew();
+  g_crew->rc.assign((size_t)ndev, 0);
+  for (int r = 0; r < ndev; r++) g_crew->th.emplace_back(crew_loop, r);
+  g_eng.ready = true; g_eng.single_process = true; g_eng.nranks = ndev; g_eng.P = 0; g_eng.Q = 0;
+  int rc = run_ranks([&](Rank& R) { return split_grid(R, P, Q); });
+  if (rc != 0) return rc;
+  g_eng.P = P; g_eng.Q = Q;
+  return 0;
+}
+
+int llacuda_dist_unique_id(void* id128) {
+  const NcclApi* n = nccl();
+  if (!n) return LLACUDA_ERR_BAD_ARG;
+  ncclUniqueId id;
+  LLA_NCCL(n->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int llacuda_dist_init_rank(int nranks, int rank, const void* id128, int P, int Q) {
+  ApiLock api_lock;
+  std::lock_guard<std::mutex> lk(g_eng_mu);
+  if (g_eng.ready) {
+    set_error(__FILE__, __LINE__, "llacuda_dist_init_rank: engine already initialised", g_eng.nranks);
+    return LLACUDA_ERR_BAD_ARG;
+  }
+  const NcclApi* n = nccl();
+  if (!n) return LLACUDA_ERR_BAD_ARG;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return LLACUDA_ERR_BAD_ARG;
+  if (P <= 0 || Q <= 0 || P * Q != nranks) choose_grid(nranks, &P, &Q);
+  const int dev = cur_dev();
+  if (dev < 0) { set_error(__FILE__, __LINE__, "no CUDA device: llacuda has no CPU fallback", -1); return LLACUDA_ERR_NO_DEVICE; }
+  g_ranks.assign(1, Rank());
+  Rank& R = g_ranks[0];
+  R.rank = rank; R.nranks = nranks; R.dev = dev;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  LLA_NCCL(n->CommInitRank(&R.world, nranks, id, rank));
+  LLA_TRY(rank_resources(R));
+  g_eng.ready = true; g_eng.single_process = false; g_eng.nranks = nranks;
+  LLA_TRY(split_grid(R, P, Q));
+  g_eng.P = P; g_eng.Q = Q;
+  return 0;
+}
+
+int llacuda_dist_set_grid(int P, int Q) {
+  ApiLock api_lock;
+  return regrid(P, Q);
+}
+
+int llacuda_dist_info(int* nranks, int* P, int* Q, int* single_process, int* rank) {
+  if (!g_eng.ready) return LLACUDA_ERR_BAD_ARG;
+  if (nranks) *nranks = g_eng.nranks;
+  if (P) *P = g_eng.P;
+  if (Q) *Q = g_eng.Q;
+  if (single_process) *single_process = g_eng.single_process ? 1 : 0;
+  if (rank) *rank = g_eng.single_process ? -1 : g_ranks[0].rank;
+  return 0;
+}
+
+int llacuda_dist_nccl_version(void) {
+  const NcclApi* n = nccl();
+  int v = 0;
+  if (n) n->GetVersion(&v);
+  return v;
+}
+
+int llacuda_dist_finalize(void) {
+  ApiLock api_lock;
+  std::lock_guard<std::mutex> lk(g_eng_mu);
+  if (!g_eng.ready) return 0;
+  const NcclApi* n = nccl();
+  if (g_eng.single_process && g_crew) {
+    { std::lock_guard<std::mutex> l2(g_crew->mu); g_crew->quit = true; }
+    g_crew->cv_go.notify_all();
+    for (auto& t : g_crew->th) t.join();
+    delete g_crew;
+    g_crew = nullptr;
+  }
+  const int prev = cur_dev();
+  for (auto& R : g_ranks) {
+    cudaSetDevice(R.dev);
+    cudaDeviceSynchronize();
+    if (n) {
+      for (auto& g : R.grids) {
+        if (g.rowc) n->CommDestroy(g.rowc);
+        if (g.colc) n->CommDestroy(g.colc);
+      }
+      if (R.world) n->CommDestroy(R.world);
+    }
+    if (R.main) cudaStreamDestroy(R.main);
+    if (R.side) cudaStreamDestroy(R.side);
+    for (auto& e : R.ev) if (e) cudaEventDestroy(e);
+    if (R.dflag) cudaFree(R.dflag);
+    if (R.hflag) cudaFreeHost(R.hflag);
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  g_ranks.clear();
+  g_eng = Engine();
+  return 0;
+}
+
+}  // extern "C"

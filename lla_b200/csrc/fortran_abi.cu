@@ -163,7 +163,9 @@ LLA_EXPORT void dgemm_(const char* transa, const char* transb, const fint* m_, c
   else if (ldc < (m > 1 ? m : 1)) bad = 13;
   if (bad) { blas_arg_error("DGEMM ", bad); return; }
   llacuda_clear_error();
-  int r = dgemm_host(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc);
+  const int64_t small = m < n ? (m < k ? m : k) : (n < k ? n : k);
+  int r = dist_route(small) ? dist_dgemm(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc)
+                            : dgemm_host(oa, ob, m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc);
   if (r != 0) blas_failure("dgemm_", r, c, ldc, m, n, sizeof(double));
 }
 
@@ -289,6 +291,12 @@ LLA_EXPORT void dgetrf_(const fint* m_, const fint* n_, double* a, const fint* l
   if (n < 0) { *info = -2; return; }
   if (lda < max1(m)) { *info = -4; return; }
   if (m == 0 || n == 0) return;
+  if (m == n && dist_route(n)) {   // LLACUDA_GPUS=N: one factorisation over the GPUs of the box
+    int inf = 0;
+    int rc = dist_dgesv(n, -1, a, lda, ipiv, nullptr, 0, &inf);
+    *info = (fint)(rc != 0 ? rc : inf);
+    return;
+  }
   int rc = dgetrf_host(m, n, a, lda, ipiv, info);
   if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
@@ -385,6 +393,12 @@ LLA_EXPORT void dgesv_(const fint* n_, const fint* nrhs_, double* a, const fint*
   if (lda < max1(n)) { *info = -4; return; }
   if (ldb < max1(n)) { *info = -7; return; }
   if (n == 0) return;
+  if (dist_route(n)) {
+    int inf = 0;
+    int rc = dist_dgesv(n, nrhs, a, lda, ipiv, b, ldb, &inf);
+    *info = (fint)(rc != 0 ? rc : inf);
+    return;
+  }
   int rc = dgesv_host(n, nrhs, a, lda, ipiv, b, ldb, info);
   if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }
@@ -431,6 +445,12 @@ LLA_EXPORT void dpotrf_(const char* uplo, const fint* n_, double* a, const fint*
   if (n < 0) { *info = -2; return; }
   if (lda < max1(n)) { *info = -4; return; }
   if (n == 0) return;
+  if (upper && dist_route(n)) {
+    int inf = 0;
+    int rc = dist_dpotrf(n, a, lda, &inf);
+    *info = (fint)(rc != 0 ? rc : inf);
+    return;
+  }
   int rc = dpotrf_host(upper, n, a, lda, info);
   if (rc != 0) { drain_streams(); stage_sync(nullptr); *info = (fint)rc; }
 }

@@ -168,6 +168,19 @@ int dpotrf_dev(bool upper, int64_t n, double* A, int64_t lda, int* info_dev, cud
 int dpotrs_dev(bool upper, int64_t n, int64_t nrhs, const double* A, int64_t lda,
                double* B, int64_t ldb, cudaStream_t st, const int* abort_flag = nullptr);
 
+// batched small solves (batched_f64.cu): one warp per n <= 32 system
+int dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t strideA, int* ipiv, double* B,
+                      int64_t strideB, int* info, int keep_lu, cudaStream_t st);
+
+// ------------------------------------------------------------------ multi-GPU routing (dist_abi.cu)
+// true when LLACUDA_GPUS=N asked for the engine and the problem is large enough: the plain Fortran symbols then
+// partition the call over the GPUs of the box (the Lisp side does not change)
+bool dist_route(int64_t n);
+int dist_dgemm(int oa, int ob, int64_t m, int64_t n, int64_t k, double alpha, const double* a, int64_t lda, const double* b,
+               int64_t ldb, double beta, double* c, int64_t ldc);
+int dist_dgesv(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ipiv, double* b, int64_t ldb, int* info);
+int dist_dpotrf(int64_t n, double* a, int64_t lda, int* info);
+
 // ------------------------------------------------------------------ layout kernels (transpose.cu)
 int dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out, int64_t ldout,
                    cudaStream_t st);   // out[c + r*ldout] = in[r + c*ldin]

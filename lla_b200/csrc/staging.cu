@@ -110,6 +110,13 @@ int region_d2h(void* host, size_t hpitch, const void* dev, size_t dpitch, size_t
 }
 }  // namespace
 
+int stage_region_h2d(void* dev, size_t dpitch, const void* host, size_t hpitch, size_t width, size_t ncols, cudaStream_t st) {
+  return region_h2d(dev, dpitch, host, hpitch, width, ncols, st);
+}
+int stage_region_d2h(void* host, size_t hpitch, const void* dev, size_t dpitch, size_t width, size_t ncols, cudaStream_t st) {
+  return region_d2h(host, hpitch, dev, dpitch, width, ncols, st);
+}
+
 int stage_sync(cudaStream_t st) {
   int rc = 0;
   for (auto& p : g_pending) {

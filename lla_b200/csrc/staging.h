@@ -40,6 +40,10 @@ int stage_download_tri(const Staged& s, void* host, int64_t ldh, bool upper, int
 // rows [r0, r1) of the columns [c0, cols)
 int stage_download_rows(const Staged& s, void* host, int64_t ldh, int64_t r0, int64_t r1, int64_t c0, cudaStream_t st);
 bool host_is_pinned(const void* p);
+// one 2-D region (ncols pieces of `width` bytes, pitches in bytes) between host and device on `st`; pageable host
+// memory goes through the pinned ring (hostpipe.cu), completed by stage_sync()
+int stage_region_h2d(void* dev, size_t dpitch, const void* host, size_t hpitch, size_t width, size_t ncols, cudaStream_t st);
+int stage_region_d2h(void* host, size_t hpitch, const void* dev, size_t dpitch, size_t width, size_t ncols, cudaStream_t st);
 // end of a host-pointer call: completes the pageable transfers this thread started through the pinned ring
 // (hostpipe.cu), then synchronises `st`
 int stage_sync(cudaStream_t st);
