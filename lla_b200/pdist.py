@@ -247,8 +247,8 @@ def pdgesv_batched(a, b, keep_lu=False):
     vec = b.ndim == 2
     bb = b[:, :, None] if vec else b
     nrhs = bb.shape[2]
-    acm = np.ascontiguousarray(np.transpose(a, (0, 2, 1)))       # column-major image per system
-    bcm = np.ascontiguousarray(np.transpose(bb, (0, 2, 1)))
+    acm = np.array(np.transpose(a, (0, 2, 1)), order="C", copy=True)       # column-major image per system (never a view)
+    bcm = np.array(np.transpose(bb, (0, 2, 1)), order="C", copy=True)
     ipiv = np.zeros((batch, n), dtype=np.int32)
     info_ = np.zeros(batch, dtype=np.int32)
     f = _f("llacuda_pdgesv_batched", [_int, _int, _i64, _vp, _vp, _vp, _vp, _int])
