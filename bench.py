@@ -111,30 +111,34 @@ def _seed(kind, I, J):
     return (kind * 1_000_003 + I) * 1_000_003 + J + 12345
 
 
-def local_image(kind, n, P, Q, rank, dev, scale=1.0, spd=False):
-    """Block-cyclic local part (image (n/Q, n/P): row j = local column j) of the seeded global n x n matrix `kind`.
-    Global block (I, J) (GEN_NB square) = scale * U[0,1) drawn from a generator seeded by (kind, I, J) only, so every
-    process grid sees the same matrix.  spd: only blocks I <= J are drawn and n is added to the diagonal -- the symmetric
+def local_image(kind, n, P, Q, rank, dev, scale=1.0, spd=False, nb=None):
+    """Block-cyclic local part (image (n/Q, n/P): row j = local column j) of the seeded global n x n matrix `kind`,
+    distributed in nb x nb blocks (default GEN_NB).  The matrix itself is defined GEN_NB block by GEN_NB block: global
+    block (I, J) = scale * U[0,1) from a generator seeded by (kind, I, J) only, so every process grid and every layout
+    block size sees the same matrix.  spd: only blocks I <= J are drawn and n is added to the diagonal -- the symmetric
     matrix named by that upper triangle is strictly diagonally dominant, hence SPD (POTRF 'U' reads nothing else)."""
     import torch
-    nb = GEN_NB
+    g0 = GEN_NB
+    nb = nb or g0
+    assert nb % g0 == 0 and n % (nb * P) == 0 and n % (nb * Q) == 0
+    sub = nb // g0
     p, q = rank // Q, rank % Q
     nblk = n // nb
-    rows = [I for I in range(nblk) if I % P == p]
-    cols = [J for J in range(nblk) if J % Q == q]
-    out = torch.zeros((len(cols) * nb, len(rows) * nb), dtype=torch.float64, device=dev)
+    rows = [I * sub + s for I in range(nblk) if I % P == p for s in range(sub)]      # global GEN_NB block rows, local order
+    cols = [J * sub + s for J in range(nblk) if J % Q == q for s in range(sub)]
+    out = torch.zeros((len(cols) * g0, len(rows) * g0), dtype=torch.float64, device=dev)
     g = torch.Generator(device=dev)
     for lj, J in enumerate(cols):
         for li, I in enumerate(rows):
             if spd and I > J:
                 continue
             g.manual_seed(_seed(kind, I, J))
-            blk = torch.rand((nb, nb), dtype=torch.float64, device=dev, generator=g)
+            blk = torch.rand((g0, g0), dtype=torch.float64, device=dev, generator=g)
             if scale != 1.0:
                 blk *= scale
             if spd and I == J:
                 blk.diagonal().add_(float(n))
-            out[lj * nb:(lj + 1) * nb, li * nb:(li + 1) * nb] = blk
+            out[lj * g0:(lj + 1) * g0, li * g0:(li + 1) * g0] = blk
     return out
 
 
@@ -249,14 +253,14 @@ def gpu_value_leg(args, rank, world, local_rank, ctl):
 
     # ---- operands, block-cyclic parts (N = 1: the whole matrix)
     Pg, Qg = gemm_grid
-    A_g = local_image(1, n, Pg, Qg, rank, dev, 10.0)
-    B_g = local_image(2, n, Pg, Qg, rank, dev, 10.0)
+    A_g = local_image(1, n, Pg, Qg, rank, dev, 10.0, nb=gemm_nb)
+    B_g = local_image(2, n, Pg, Qg, rank, dev, 10.0, nb=gemm_nb)
     C_g = torch.zeros_like(A_g)
     Pl, Ql = lu_grid
-    A_l = A_g if (Pl, Ql) == (Pg, Qg) else local_image(1, n, Pl, Ql, rank, dev, 10.0)
+    A_l = A_g if world == 1 else local_image(1, n, Pl, Ql, rank, dev, 10.0, nb=DIST_NB)
     W_l = torch.empty_like(A_l)
     Pc, Qc = chol_grid
-    S_c = local_image(3, n, Pc, Qc, rank, dev, 1.0, spd=True)
+    S_c = local_image(3, n, Pc, Qc, rank, dev, 1.0, spd=True, nb=DIST_NB)
     W_c = torch.empty_like(S_c)
     RHS = rhs_image(n, nrhs, dev)
     X = torch.empty_like(RHS)
@@ -342,23 +346,20 @@ def gpu_value_leg(args, rank, world, local_rank, ctl):
                                            (n * EPS * torch.linalg.norm(Am) * torch.linalg.norm(Xm))).item()
         # GEMM: 8 local rows of my part of C against fp64 dot products of the whole operands
         fullB = B_g if world == 1 else local_image(2, n, 1, 1, 0, dev, 10.0)
-        bcg = PD.BlockCyclic(n, n, GEN_NB if world > 1 else n, Pg, Qg, 0) if world > 1 else None
         sel = torch.randint(0, C_g.shape[1], (8,), generator=torch.Generator().manual_seed(5)).tolist()
         if world == 1:
-            # N = 1 computes C_img = (B_img as CM) (A_img as CM): C_img^T = A_img^T B_img^T, i.e. C_img = B... as LLA's mm
-            ref = (fullB.t()[sel, :] @ fullA.t()).t() if False else None
-            # column-major product M = B_cm A_cm with X_cm = X_img^T: M = B_img^T A_img^T => M_img = A_img B_img
-            ref_img_cols = fullA[:, :] @ fullB[:, sel] if False else None
-            ref = (fullA @ fullB)[:, sel] if n <= 4096 else fullA @ fullB[:, sel]
+            # LLA's mm: dgemm(N, N) on the untransposed row-major buffers, C_cm = B_cm A_cm, i.e. C_img = A_img B_img
+            ref = fullA @ fullB[:, sel]
             got = C_g[:, sel]
             scale = torch.linalg.norm(fullA, dim=1)[:, None] * torch.linalg.norm(fullB[:, sel], dim=0)[None, :]
         else:
-            rows_g = torch.as_tensor(bcg.local_rows(), device=dev)[sel]                # global rows of my local rows
+            # C = A B; images X_img[j, i] = X(i, j): C(rows, cols)^T = B_img[cols, :] A_img[:, rows]; 8 of my local rows
+            bcg = PD.BlockCyclic(n, n, gemm_nb, Pg, Qg, 0)
+            rows_g = torch.as_tensor(bcg.local_rows(), device=dev)[sel]
             cols_g = torch.as_tensor(bcg.local_cols(), device=dev)
-            # C = A B (column-major world): C(i, j) = sum_k A(i, k) B(k, j); images: X_img[j, i] = X(i, j)
-            Arow = fullA[:, rows_g]                      # (n, 8): A(rows, :)^T
-            Bcol = fullB[cols_g, :]                      # (nloc, n): B(:, cols)^T
-            ref = Bcol @ Arow                            # (nloc, 8): C(rows, cols)^T
+            Arow = fullA[:, rows_g]
+            Bcol = fullB[cols_g, :]
+            ref = Bcol @ Arow
             got = C_g[:, sel]
             scale = torch.linalg.norm(Bcol, dim=1)[:, None] * torch.linalg.norm(Arow, dim=0)[None, :]
         parity["mm_max_err_over_bound"] = (torch.abs(got - ref) / (4 * (n ** 0.5) * EPS * scale)).max().item()
@@ -492,8 +493,8 @@ def n32768_leg(args, rank, world, local_rank):
 
     Pg, Qg = PD.default_grid(world)
     nbg = 2048
-    A = local_image(11, n, Pg, Qg, rank, dev, 2.0).sub_(1.0)
-    B = local_image(12, n, Pg, Qg, rank, dev, 2.0).sub_(1.0)
+    A = local_image(11, n, Pg, Qg, rank, dev, 2.0, nb=nbg).sub_(1.0)
+    B = local_image(12, n, Pg, Qg, rank, dev, 2.0, nb=nbg).sub_(1.0)
     C = torch.empty_like(A)
     if dist_mode:
         PD.set_grid(Pg, Qg)
@@ -504,13 +505,13 @@ def n32768_leg(args, rank, world, local_rank):
     del C
     if not args.skip_zgemm:
         # complex operands: re = the real matrices above, im = a second draw
-        Az = torch.complex(A, local_image(13, n, Pg, Qg, rank, dev, 2.0).sub_(1.0))
+        Az = torch.complex(A, local_image(13, n, Pg, Qg, rank, dev, 2.0, nb=nbg).sub_(1.0))
         del A
-        Bz = torch.complex(B, local_image(14, n, Pg, Qg, rank, dev, 2.0).sub_(1.0))
+        Bz = torch.complex(B, local_image(14, n, Pg, Qg, rank, dev, 2.0, nb=nbg).sub_(1.0))
         del B
         Cz = torch.empty_like(Az)
         if dist_mode:
-            ms = run(lambda: PD.pzgemm_local(n, n, n, 1024, 1.0, Az.data_ptr(), n // Pg, Bz.data_ptr(), n // Pg, 0.0, Cz.data_ptr(), n // Pg), reps=2)
+            ms = run(lambda: PD.pzgemm_local(n, n, n, nbg, 1.0, Az.data_ptr(), n // Pg, Bz.data_ptr(), n // Pg, 0.0, Cz.data_ptr(), n // Pg), reps=2)
         else:
             ms = run(lambda: D.zgemm("N", "N", n, n, n, 1 + 0j, Az.data_ptr(), n, Bz.data_ptr(), n, 0j, Cz.data_ptr(), n), reps=2)
         out["zgemm"] = {"ms": ms, "gflops": 8.0 * n ** 3 / ms / 1e6}
@@ -519,7 +520,7 @@ def n32768_leg(args, rank, world, local_rank):
         del A, B
     torch.cuda.empty_cache()
     Pc, Qc = _grid_env("LLACUDA_CHOL_GRID", world, (1, world))
-    S = local_image(15, n, Pc, Qc, rank, dev, 1.0, spd=True)
+    S = local_image(15, n, Pc, Qc, rank, dev, 1.0, spd=True, nb=DIST_NB)
     W = torch.empty_like(S)
     infos = []
 
@@ -537,7 +538,7 @@ def n32768_leg(args, rank, world, local_rank):
     del S, W
     torch.cuda.empty_cache()
     Pl, Ql = _grid_env("LLACUDA_LU_GRID", world, (1, world))
-    A = local_image(11, n, Pl, Ql, rank, dev, 10.0)
+    A = local_image(11, n, Pl, Ql, rank, dev, 10.0, nb=DIST_NB)
     W = torch.empty_like(A)
     ipiv = torch.zeros(n, dtype=torch.int32, device=dev)
     if dist_mode:

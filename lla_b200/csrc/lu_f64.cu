@@ -28,8 +28,11 @@
 
 namespace llacuda {
 
-constexpr int PW = 32;     // leaf panel width (columns held in registers per row)
-constexpr int PR = 128;    // rows (= threads) per CTA
+constexpr int PW = 32;     // leaf panel width (one lane per column when a row travels)
+// rows (= threads) per CTA: a template parameter of the panel kernel.  128 rows: up to 128 CTAs exchange through L2 every
+// column and sit next to the trailing update's GEMM CTAs on as many SMs; 512 rows: a quarter of the CTAs (the per-column
+// all-to-all is the chain of the factorisation: tools/mb/xchg.cu, 3.7k cycles for 128 CTAs, 2.1k for 48, 0.9k for one)
+// and a quarter of the SMs taken from the update.  LLACUDA_LU_PR = 128 | 256 | 512 selects (measured default below).
 
 // Cross-CTA exchange uses self-validating 8-byte words (32 bits of payload + a 32-bit tag, the
 // NCCL "LL" idea): an aligned 8-byte store is single-copy atomic, so a reader that sees the
@@ -65,8 +68,7 @@ __device__ __forceinline__ bool ll_load(const LLDouble* p, unsigned tag, double&
   return ok;
 }
 
-constexpr int PPITCH = PR + 1;                       // shared-memory pitch of one panel column
-constexpr size_t PANEL_SMEM = (size_t)PW * PPITCH * sizeof(double);
+template <int PR> constexpr size_t panel_smem() { return (size_t)PW * (PR + 1) * sizeof(double); }
 
 // multiplier of DGETF2: reciprocal scaling when |pivot| >= sfmin, division otherwise, nothing for a zero pivot
 __device__ __forceinline__ double lu_multiplier(double a, double piv, double rinv) {
@@ -86,12 +88,13 @@ __device__ __forceinline__ double lu_multiplier(double a, double piv, double rin
 // travel through L2.  The arithmetic is unchanged: the update rounds the product and the subtraction
 // separately, exactly as DGETF2/DGER do, so a matrix that fits one leaf (n <= 32) is factored
 // bit-identically to the reference algorithm and exact ties between pivot candidates resolve the same way.
-template <bool DBG>
-__global__ void __launch_bounds__(PR, 3) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
+template <int PR, bool DBG>
+__global__ void __launch_bounds__(PR, PR >= 512 ? 1 : (PR >= 256 ? 2 : 3)) lla_dgetf2_panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int w,
                                                                  int64_t off, int* __restrict__ ipiv, int* __restrict__ info,
                                                                  PanelHdr* __restrict__ hdrs, PanelRow* __restrict__ rows,
                                                                  PanelRow* __restrict__ rowj, unsigned epoch,
                                                                  unsigned long long* __restrict__ dbg) {
+  constexpr int PPITCH = PR + 1;   // shared-memory pitch of one panel column
   extern __shared__ __align__(16) double S[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -491,17 +494,41 @@ struct LuCtx {
 
 static std::atomic<unsigned> g_panel_epoch{1};
 
-static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
-  // panel = A[j0 : j0+m, j0 : j0+w]
-  double* P = L.A + j0 + j0 * L.lda;
+static int panel_rows() {   // rows per CTA of the panel kernel
+  static int pr = 0;
+  if (pr == 0) {
+    const char* e = getenv("LLACUDA_LU_PR");
+    pr = e ? atoi(e) : 512;
+    if (pr != 128 && pr != 256 && pr != 512) pr = 512;
+  }
+  return pr;
+}
+
+template <int PR>
+static int launch_panel(const LuCtx& L, double* P, int64_t m, int w, int64_t off, unsigned epoch, unsigned long long* dbg) {
+  static DeviceOnce once;
+  if (once.first()) {
+    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<PR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<PR>()));
+    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<PR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<PR>()));
+  }
   int G = (int)((m + PR - 1) / PR);
-  int64_t m_ = m, lda_ = L.lda, off_ = j0;
+  int64_t m_ = m, lda_ = L.lda, off_ = off;
   int w_ = w;
   int* ipiv_ = L.ipiv;
   int* info_ = L.info;
   PanelHdr* h_ = L.hdrs;
   PanelRow* r_ = L.rows;
   PanelRow* rj_ = L.rowj;
+  void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &h_, &r_, &rj_, &epoch, &dbg};
+  LLA_CUDA(cudaLaunchCooperativeKernel(dbg ? (void*)lla_dgetf2_panel_kernel<PR, true> : (void*)lla_dgetf2_panel_kernel<PR, false>, dim3(G),
+                                       dim3(PR), args, panel_smem<PR>(), L.st));
+  count_launch();
+  return 0;
+}
+
+static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
+  // panel = A[j0 : j0+m, j0 : j0+w]
+  double* P = L.A + j0 + j0 * L.lda;
   unsigned epoch = g_panel_epoch.fetch_add(1) & 0x03ffffffu;
   if (epoch == 0) epoch = g_panel_epoch.fetch_add(1) & 0x03ffffffu;
   // LLACUDA_PANEL_DBG=1: per-column phase breakdown of the exchange (instrumented instantiation of the kernel)
@@ -520,9 +547,10 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   }
   static const bool leaf_trace = getenv("LLACUDA_TRACE_LEAF") != nullptr;
   if (leaf_trace) trace_mark(L.st, "lu.leaf>", j0, m);
-  void* args[] = {&P, &lda_, &m_, &w_, &off_, &ipiv_, &info_, &h_, &r_, &rj_, &epoch, &dbg};
-  LLA_CUDA(cudaLaunchCooperativeKernel(dbg ? (void*)lla_dgetf2_panel_kernel<true> : (void*)lla_dgetf2_panel_kernel<false>, dim3(G), dim3(PR), args, PANEL_SMEM, L.st));
-  count_launch();
+  const int pr = panel_rows();
+  if (pr == 128) LLA_TRY(launch_panel<128>(L, P, m, w, j0, epoch, dbg));
+  else if (pr == 256) LLA_TRY(launch_panel<256>(L, P, m, w, j0, epoch, dbg));
+  else LLA_TRY(launch_panel<512>(L, P, m, w, j0, epoch, dbg));
   if (leaf_trace) trace_mark(L.st, "lu.leafK<", j0, m);
   // interchange the other columns of the swap window now: [swap_c0, j0) and [j0+w, swap_c1)
   int64_t npiv = m < w ? m : w;
@@ -655,14 +683,22 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   LLA_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
   if (m <= 0 || n <= 0) return 0;
-  int maxG = (int)((m + PR - 1) / PR);
+  const int pr = panel_rows();
+  int maxG = (int)((m + pr - 1) / pr);
   // co-residency bound of the cooperative panel kernel
   static int per_sm_dev[MAX_DEV] = {};
   int& per_sm = per_sm_dev[c->device];
   if (per_sm == 0) {
-    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel<false>, PR, PANEL_SMEM));
+    if (pr == 128) {
+      LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<128>()));
+      LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel<128, false>, 128, panel_smem<128>()));
+    } else if (pr == 256) {
+      LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<256>()));
+      LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel<256, false>, 256, panel_smem<256>()));
+    } else {
+      LLA_CUDA(cudaFuncSetAttribute(lla_dgetf2_panel_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<512>()));
+      LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel<512, false>, 512, panel_smem<512>()));
+    }
   }
   if ((int64_t)per_sm * c->sm_count < maxG) {
     set_error(__FILE__, __LINE__, "dgetrf: panel too tall for one cooperative launch", (int)m);
