@@ -216,9 +216,9 @@ def cpu_leg(n, steps, warmup, nrhs=NRHS, seed=0, operands=None):
 
 
 def cpu_n_for_budget(n, passes, budget_s):
-    """the workload's n unless `passes` passes at ~25 GFLOP/s per core would exceed the budget"""
+    """the workload's n unless `passes` passes at ~50 GFLOP/s per core (measured on the GPU box's host: 80) would exceed the budget"""
     cores = os.cpu_count() or 1
-    while n > 2048 and sum(flops(n).values()) * passes / (25e9 * cores) > budget_s:
+    while n > 2048 and sum(flops(n).values()) * passes / (50e9 * cores) > budget_s:
         n //= 2
     return n
 

@@ -230,6 +230,85 @@ void llacuda_dgetrs_rm(const llacuda_int* n, const llacuda_int* nrhs, const doub
 void llacuda_dpotrs_rm(const llacuda_int* n, const llacuda_int* nrhs, const double* l, const llacuda_int* lda, double* b,
                        const llacuda_int* ldb, llacuda_int* info);
 
+/* ------------------------------------------------------------------ single, complex-single and complex-double types
+ * LLA's lu / solve / cholesky / mm-hermitian% dispatch on the common float type of their operands through the four-way
+ * ECASE of src/fortran-call.lisp:428-439 (call sites src/linear-algebra.lisp:62-76,227-234,269-276,282-289,296-315,670-674):
+ * same argument lists as the d-symbols above, complex operands interleaved (re, im).  Pivot rule of the complex types: first
+ * maximum of |re| + |im| (IZAMAX / ICAMAX).  HERK takes REAL alpha / beta; LLA hands cells of the matrix type, whose
+ * leading real part is what gets read. */
+void sgetrf_(const llacuda_int* m, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void sgetrs_(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, void* b, const llacuda_int* ldb, llacuda_int* info);
+void sgesv_(const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, llacuda_int* ipiv, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void spotrf_(const char* uplo, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* info);
+void spotrs_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda, void* b,
+             const llacuda_int* ldb, llacuda_int* info);
+void sposv_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_sgetrf(const llacuda_int* m, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void llacuda_sgetrs(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, void* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_sgesv(const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, llacuda_int* ipiv, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_spotrf(const char* uplo, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_spotrs(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda, void* b,
+             const llacuda_int* ldb, llacuda_int* info);
+void llacuda_sposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void cgetrf_(const llacuda_int* m, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void cgetrs_(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, void* b, const llacuda_int* ldb, llacuda_int* info);
+void cgesv_(const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, llacuda_int* ipiv, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void cpotrf_(const char* uplo, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* info);
+void cpotrs_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda, void* b,
+             const llacuda_int* ldb, llacuda_int* info);
+void cposv_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_cgetrf(const llacuda_int* m, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void llacuda_cgetrs(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, void* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_cgesv(const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, llacuda_int* ipiv, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_cpotrf(const char* uplo, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_cpotrs(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda, void* b,
+             const llacuda_int* ldb, llacuda_int* info);
+void llacuda_cposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void zgetrf_(const llacuda_int* m, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void zgetrs_(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, void* b, const llacuda_int* ldb, llacuda_int* info);
+void zgesv_(const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, llacuda_int* ipiv, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void zpotrf_(const char* uplo, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* info);
+void zpotrs_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda, void* b,
+             const llacuda_int* ldb, llacuda_int* info);
+void zposv_(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_zgetrf(const llacuda_int* m, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* ipiv, llacuda_int* info);
+void llacuda_zgetrs(const char* trans, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda,
+             const llacuda_int* ipiv, void* b, const llacuda_int* ldb, llacuda_int* info);
+void llacuda_zgesv(const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, llacuda_int* ipiv, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void llacuda_zpotrf(const char* uplo, const llacuda_int* n, void* a, const llacuda_int* lda, llacuda_int* info);
+void llacuda_zpotrs(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, const void* a, const llacuda_int* lda, void* b,
+             const llacuda_int* ldb, llacuda_int* info);
+void llacuda_zposv(const char* uplo, const llacuda_int* n, const llacuda_int* nrhs, void* a, const llacuda_int* lda, void* b,
+            const llacuda_int* ldb, llacuda_int* info);
+void ssyrk_(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const float* alpha, const void* a,
+            const llacuda_int* lda, const float* beta, void* c, const llacuda_int* ldc);
+void cherk_(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const float* alpha, const void* a,
+            const llacuda_int* lda, const float* beta, void* c, const llacuda_int* ldc);
+void zherk_(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const double* alpha, const void* a,
+            const llacuda_int* lda, const double* beta, void* c, const llacuda_int* ldc);
+void llacuda_ssyrk(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const float* alpha,
+                   const void* a, const llacuda_int* lda, const float* beta, void* c, const llacuda_int* ldc);
+void llacuda_cherk(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const float* alpha,
+                   const void* a, const llacuda_int* lda, const float* beta, void* c, const llacuda_int* ldc);
+void llacuda_zherk(const char* uplo, const char* trans, const llacuda_int* n, const llacuda_int* k, const double* alpha,
+                   const void* a, const llacuda_int* lda, const double* beta, void* c, const llacuda_int* ldc);
+
 /* ------------------------------------------------------------------ group 4: one problem over the GPUs of one box
  * BASELINE.json north_star: "Large GEMM and blocked LU/Cholesky are partitioned across one 8xB200 box as a 2D block-cyclic
  * layout, broadcasting panels with NCCL over NVLink; batched small solves shard one batch slice per GPU ... The Lisp API

@@ -32,7 +32,8 @@ constexpr int PW = 32;     // leaf panel width (one lane per column when a row t
 // rows (= threads) per CTA: a template parameter of the panel kernel.  128 rows: up to 128 CTAs exchange through L2 every
 // column and sit next to the trailing update's GEMM CTAs on as many SMs; 512 rows: a quarter of the CTAs (the per-column
 // all-to-all is the chain of the factorisation: tools/mb/xchg.cu, 3.7k cycles for 128 CTAs, 2.1k for 48, 0.9k for one)
-// and a quarter of the SMs taken from the update.  LLACUDA_LU_PR = 128 | 256 | 512 selects (measured default below).
+// and a quarter of the SMs taken from the update -- but the CTA-internal barriers and reductions over 16 warps cost what
+// the smaller exchange saves (profiles/r02_lu_rows_per_cta.md).  LLACUDA_LU_PR = 128 | 256 | 512 selects; default 128.
 
 // Cross-CTA exchange uses self-validating 8-byte words (32 bits of payload + a 32-bit tag, the
 // NCCL "LL" idea): an aligned 8-byte store is single-copy atomic, so a reader that sees the
@@ -498,8 +499,8 @@ static int panel_rows() {   // rows per CTA of the panel kernel
   static int pr = 0;
   if (pr == 0) {
     const char* e = getenv("LLACUDA_LU_PR");
-    pr = e ? atoi(e) : 512;
-    if (pr != 128 && pr != 256 && pr != 512) pr = 512;
+    pr = e ? atoi(e) : 128;   // measured on B200, dgetrf n = 16384 / 8192: 128 rows 147.5 / 39.6 ms, 256: 146.9 / 41.1, 512: 151.9 / 44.2
+    if (pr != 128 && pr != 256 && pr != 512) pr = 128;
   }
   return pr;
 }

@@ -389,8 +389,10 @@ def mm_hermitian(a, transpose_left: bool) -> Hermitian:
     am = _as_memory(a, t)
     c = np.zeros((dim_c, dim_c), dtype=_DTYPES[t])
     (_k1, pone), (_k0, pzero) = _atom(1, t), _atom(0, t)
-    _fn(t, "syrk")(_chr("U"), _chr("N" if transpose_left else "C"), _int(dim_c), _int(other), pone, _ptr(am),
-                   _int(a1), pzero, _ptr(c), _int(dim_c))
+    # ("syrk" "herk"): SYRK for real arrays, HERK for complex ones; alpha / beta travel as cells of the matrix type
+    name = "herk" if t in (COMPLEX_SINGLE, COMPLEX_DOUBLE) else "syrk"
+    _fn(t, name)(_chr("U"), _chr("N" if transpose_left else "C"), _int(dim_c), _int(other), pone, _ptr(am),
+                 _int(a1), pzero, _ptr(c), _int(dim_c))
     _check_device_error()
     return Hermitian(c)
 

@@ -356,14 +356,15 @@ def mm_hermitian(a, transpose_left: bool, be: Backend):
     a0, a1 = a.shape
     dim_c, other = (a1, a0) if transpose_left else (a0, a1)
     t = common_float_type(a)
-    assert t in (SINGLE, DOUBLE), "complex arrays go through herk (out of scope)"
     amem = copy_array_to_memory(a, t)
     c = np.zeros((dim_c, dim_c), dtype=_DTYPES[t])
     (_k1, one), (_k0, zero) = _atom(1, t), _atom(0, t)
-    be.fn(t, "syrk")(_chr("U"), _chr("N" if transpose_left else "C"), _int(dim_c), _int(other), one,
-                     _ptr(amem), _int(a1), zero, _ptr(c), _int(dim_c))
+    # ("syrk" "herk"): complex arrays go to HERK, which reads the leading real part of the alpha / beta cells
+    name = "herk" if t in (COMPLEX_SINGLE, COMPLEX_DOUBLE) else "syrk"
+    be.fn(t, name)(_chr("U"), _chr("N" if transpose_left else "C"), _int(dim_c), _int(other), one,
+                   _ptr(amem), _int(a1), zero, _ptr(c), _int(dim_c))
     low = np.tril(c)
-    return low + np.tril(c, -1).T          # hermitian-matrix: the lower triangle defines the matrix
+    return low + np.tril(c, -1).conj().T   # hermitian-matrix: the lower triangle defines the matrix
 
 
 def solve_hermitian(a, b, be: Backend):

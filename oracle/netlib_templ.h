@@ -284,6 +284,28 @@ void PFX(syrk_)(const char *uplo, const char *trans, const int *n_, const int *k
   }
 }
 
+/* xHERK <- mm-hermitian% on complex arrays, src/linear-algebra.lisp:62-76 ("syrk" "herk"): C <- alpha A A^H + beta C
+ * (trans = 'N') or alpha A^H A + beta C (trans = 'C'), alpha / beta REAL, only the uplo triangle referenced, the
+ * diagonal kept real (netlib zherk.f loop order: per column, the conjugated factor first).  For the real types the
+ * symbol is an alias of SYRK. */
+void PFX(herk_)(const char *uplo, const char *trans, const int *n_, const int *k_, const R *alpha_, const T *a,
+                const int *lda_, const R *beta_, T *c, const int *ldc_) {
+  int64_t n = *n_, k = *k_, lda = *lda_, ldc = *ldc_;
+  R alpha = *alpha_, beta = *beta_;
+  int upper = PFX(lsame)(*uplo, 'U'), notr = PFX(lsame)(*trans, 'N');
+  for (int64_t j = 0; j < n; j++) {
+    int64_t i0 = upper ? 0 : j, i1 = upper ? j + 1 : n;
+    for (int64_t i = i0; i < i1; i++) {
+      T s = 0;
+      if (notr) { for (int64_t l = 0; l < k; l++) s += a[i + l * lda] * CONJ(a[j + l * lda]); }
+      else { for (int64_t l = 0; l < k; l++) s += CONJ(a[l + i * lda]) * a[l + j * lda]; }
+      T v = (beta == (R)0) ? alpha * s : alpha * s + beta * c[i + j * ldc];
+      if (i == j) v = REAL(v);
+      c[i + j * ldc] = v;
+    }
+  }
+}
+
 /* op(A) X = alpha B (side 'L') or X op(A) = alpha B (side 'R'); B (m x n) is overwritten by X. */
 void PFX(trsm_)(const char *side, const char *uplo, const char *transa, const char *diag, const int *m_, const int *n_,
                 const T *alpha_, const T *a, const int *lda_, T *b, const int *ldb_) {
