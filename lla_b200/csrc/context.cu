@@ -182,6 +182,9 @@ void* stream_scratch(cudaStream_t st, size_t bytes) {
 static thread_local const RowsFinalHook* g_rows_hook = nullptr;
 void set_rows_final_hook(const RowsFinalHook* h) { g_rows_hook = h; }
 const RowsFinalHook* rows_final_hook() { return g_rows_hook; }
+static thread_local const RangeReadyHook* g_ready_hook = nullptr;
+void set_range_ready_hook(const RangeReadyHook* h) { g_ready_hook = h; }
+const RangeReadyHook* range_ready_hook() { return g_ready_hook; }
 
 int DevBuf::alloc(size_t n) {
   if (n == 0) n = 16;

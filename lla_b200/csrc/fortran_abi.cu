@@ -248,6 +248,74 @@ struct RowSender {
   }
 };
 
+// The way in, block by block behind the drivers' RangeReadyHook: column blocks for LU, block rows of the upper triangle
+// for Cholesky.  Page-locked callers: every block is queued at once on the h2d stream (asynchronous), the hook only
+// makes the consumer stream wait for the blocks it is about to touch.  Pageable callers (LLA): a block is staged through
+// the pinned ring when the driver first asks for it -- the calling thread then stages block i + 1 while the GPU
+// already works on block i.
+struct BlockUploader {
+  Staged* s = nullptr;
+  const double* host = nullptr;
+  int64_t ldh = 0, chunk = 1024, total = 0;
+  bool by_rows = false;            // Cholesky 'U': rows [r0, r1) x columns [r0, n)
+  cudaStream_t sh = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<char> sent;
+  RangeReadyHook hook;
+  bool armed = false;
+  int send(int64_t i) {
+    if (sent[(size_t)i]) return 0;
+    const int64_t a = i * chunk, b = a + chunk < total ? a + chunk : total;
+    if (by_rows) LLA_TRY(stage_upload_block(*s, host, ldh, a, b, a, s->cols, sh));
+    else LLA_TRY(stage_upload_cols(*s, host, ldh, a, b, sh));
+    LLA_CUDA(cudaEventRecord(ev[(size_t)i], sh));
+    sent[(size_t)i] = 1;
+    return 0;
+  }
+  int arm(Staged& st, const double* h, int64_t ld, bool rows, cudaStream_t h2d, cudaStream_t after) {
+    s = &st; host = h; ldh = ld; by_rows = rows; sh = h2d;
+    total = rows ? st.rows : st.cols;
+    const int64_t nchunk = (total + chunk - 1) / chunk;
+    ev.assign((size_t)nchunk, nullptr);
+    sent.assign((size_t)nchunk, 0);
+    for (auto& e : ev) LLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t start;
+    LLA_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    LLA_CUDA(cudaEventRecord(start, after));       // the staging buffer may still be in use by earlier work on `after`
+    LLA_CUDA(cudaStreamWaitEvent(sh, start, 0));
+    cudaEventDestroy(start);
+    if (host_is_pinned(h))
+      for (int64_t i = 0; i < nchunk; i++) LLA_TRY(send(i));
+    hook.fn = &BlockUploader::ready; hook.user = this;
+    set_range_ready_hook(&hook);
+    armed = true;
+    return 0;
+  }
+  static int ready(void* user, int64_t lo, int64_t hi, cudaStream_t st) {
+    BlockUploader* self = (BlockUploader*)user;
+    if (hi > self->total) hi = self->total;
+    for (int64_t i = lo / self->chunk; i * self->chunk < hi; i++) {
+      LLA_TRY(self->send(i));
+      LLA_CUDA(cudaStreamWaitEvent(st, self->ev[(size_t)i], 0));
+    }
+    return 0;
+  }
+  // after the driver: whatever it did not ask for (nothing, normally) and a join on `st`
+  int finish(cudaStream_t st) {
+    disarm();
+    for (size_t i = 0; i < ev.size(); i++) {
+      LLA_TRY(send((int64_t)i));
+      LLA_CUDA(cudaStreamWaitEvent(st, ev[i], 0));
+    }
+    return 0;
+  }
+  void disarm() { if (armed) { set_range_ready_hook(nullptr); armed = false; } }
+  ~BlockUploader() {
+    disarm();
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+  }
+};
+
 // reads the device INFO word back; a CUDA failure overrides it with the out-of-band code
 
 static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, fint* ipiv, fint* info) {
@@ -262,13 +330,16 @@ static int dgetrf_host(int64_t m, int64_t n, double* a, int64_t lda, fint* ipiv,
   LLA_TRY(stage_alloc(sa, m, n, sizeof(double)));
   LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(mn)));
   LLA_TRY(inf.alloc(sizeof(int)));
-  LLA_TRY(stage_upload(sa, a, lda, st));
+  BlockUploader up;
+  LLA_TRY(up.arm(sa, a, lda, false, cx->h2d, st));
   tm.mark(1);
   RowSender rs;
   LLA_TRY(rs.arm(sa, a, lda, cx->d2h, false));
   int rc = dgetrf_dev(m, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st);
   rs.disarm();
+  up.disarm();
   LLA_TRY(rc);
+  LLA_TRY(up.finish(st));
   tm.mark(2);
   LLA_TRY(stage_download_rows(sa, a, lda, rs.sent_upto, m, 0, st));
   LLA_CUDA(cudaStreamSynchronize(cx->d2h));
@@ -357,14 +428,17 @@ static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ipi
   LLA_TRY(stage_alloc(sb, n, nrhs, sizeof(double)));
   LLA_TRY(piv.alloc(sizeof(int) * (size_t)max1(n)));
   LLA_TRY(inf.alloc(sizeof(int)));
-  LLA_TRY(stage_upload(sa, a, lda, st));
   LLA_TRY(stage_upload(sb, b, ldb, st));
+  BlockUploader up;
+  LLA_TRY(up.arm(sa, a, lda, false, cx->h2d, st));
   tm.mark(1);
   RowSender rs;
   LLA_TRY(rs.arm(sa, a, lda, cx->d2h, false));
   int rc = dgetrf_dev(n, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st);
   rs.disarm();
+  up.disarm();
   LLA_TRY(rc);
+  LLA_TRY(up.finish(st));
   // DGESV solves only when the factorisation reported INFO = 0: the INFO word is the abort flag
   LLA_TRY(dgetrs_dev(0, n, nrhs, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st,
                      (const int*)inf.p));
@@ -415,13 +489,17 @@ static int dpotrf_host(bool upper, int64_t n, double* a, int64_t lda, fint* info
   LLA_TRY(inf.alloc(sizeof(int)));
   // only the named triangle crosses PCIe, in both directions: the other one is neither read nor written
   // (LAPACK: "not referenced"), so the caller's bytes there stay as they are
-  LLA_TRY(stage_upload_tri(sa, a, lda, upper, st));
+  BlockUploader up;
+  if (upper) LLA_TRY(up.arm(sa, a, lda, true, cx->h2d, st));   // block rows of the upper triangle, behind the driver's hook
+  else LLA_TRY(stage_upload_tri(sa, a, lda, upper, st));
   tm.mark(1);
   RowSender rs;
   if (upper) LLA_TRY(rs.arm(sa, a, lda, cx->d2h, true));
   int rc = dpotrf_dev(upper, n, sa.ptr<double>(), sa.ld, (int*)inf.p, st);
   rs.disarm();
+  up.disarm();
   LLA_TRY(rc);
+  if (upper) LLA_TRY(up.finish(st));
   tm.mark(2);
   LLA_TRY(stage_download_tri(sa, a, lda, upper, rs.sent_upto, st));
   LLA_CUDA(cudaStreamSynchronize(cx->d2h));

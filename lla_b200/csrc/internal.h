@@ -156,6 +156,16 @@ struct RowsFinalHook {
   int (*fn)(void* user, int64_t r0, int64_t r1, cudaStream_t a, cudaStream_t b);
   void* user;
 };
+// The mirror image on the way in: columns (dgetrf) or rows of the upper triangle (dpotrf 'U') [lo, hi) are about to be
+// touched for the first time by work queued on `st`.  The host-pointer entry points upload the matrix in blocks behind
+// this hook, so the transfer of the rest overlaps the first block step (its update is separable by column / row block).
+struct RangeReadyHook {
+  int (*fn)(void* user, int64_t lo, int64_t hi, cudaStream_t st);
+  void* user;
+};
+void set_range_ready_hook(const RangeReadyHook* h);   // nullptr clears; thread-local, valid for the next dgetrf_dev / dpotrf_dev
+const RangeReadyHook* range_ready_hook();
+constexpr int64_t READY_BLOCK = 2048;                  // granularity the drivers announce ranges in
 void set_rows_final_hook(const RowsFinalHook* h);   // nullptr clears; valid for the next dgetrf_dev / dpotrf_dev only
 const RowsFinalHook* rows_final_hook();
 int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st);

@@ -625,7 +625,9 @@ static int lu_blocked(LuCtx L) {
   if (NB_env < 0) { const char* e = getenv("LLACUDA_LU_NB"); NB_env = e ? atoi(e) : 0; }
   const int64_t NB = NB_env > 0 ? NB_env : 512;
   const int64_t mn = L.M < L.N ? L.M : L.N;
+  const RangeReadyHook* ready = range_ready_hook();
   if (mn <= 2 * NB) {
+    if (ready) LLA_TRY(ready->fn(ready->user, 0, L.N, L.st));
     L.swap_c0 = 0; L.swap_c1 = L.N;
     return lu_rec(L, 0, L.M, L.N);
   }
@@ -639,6 +641,7 @@ static int lu_blocked(LuCtx L) {
     // ---- panel k on s2
     LuCtx P = L;
     P.st = s2; P.swap_c0 = k; P.swap_c1 = k + kb;
+    if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
     trace_mark(s2, "lu.panel>", k, kb);
     LLA_TRY(lu_rec(P, k, L.M - k, kb));
     trace_mark(s2, "lu.panel<", k, kb);
@@ -657,6 +660,7 @@ static int lu_blocked(LuCtx L) {
     const int64_t next_kb = (k + kb < mn) ? ((mn - c0) < NB ? (mn - c0) : NB) : 0;
     const int64_t c1 = c0 + next_kb;
     trace_mark(s1, "lu.updA>", k, c1 - c0);
+    if (ready && k == 0 && c1 > c0) LLA_TRY(ready->fn(ready->user, c0, c1, s1));
     LLA_TRY(lu_update_cols(L, k, kb, c0, c1, s1));
     trace_mark(s1, "lu.updA<", k, c1 - c0);
     LLA_CUDA(cudaEventRecord(ev_a, s1));
@@ -666,6 +670,14 @@ static int lu_blocked(LuCtx L) {
     static int reserve = -1;
     if (reserve < 0) { const char* e = getenv("LLACUDA_LU_RESERVE"); reserve = e ? atoi(e) : 0; }  // measured: no gain on B200 (profiles/r01_lu_tuning.txt), off by default
     const bool overlap = (c1 < L.N) && (k + kb < mn);
+    if (ready && k == 0) {
+      // first step: the update is separable by column block, so each block starts as soon as its columns are on the device
+      for (int64_t cc = c1; cc < L.N; cc += READY_BLOCK) {
+        const int64_t ce = cc + READY_BLOCK < L.N ? cc + READY_BLOCK : L.N;
+        LLA_TRY(ready->fn(ready->user, cc, ce, s1));
+        LLA_TRY(lu_update_cols(L, k, kb, cc, ce, s1));
+      }
+    } else
     LLA_TRY(lu_update_cols(L, k, kb, c1, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
     trace_mark(s1, "lu.updB<", k, L.N - c1);
     LLA_CUDA(cudaEventRecord(ev_b, s1));

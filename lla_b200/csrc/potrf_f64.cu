@@ -92,7 +92,11 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
   static int64_t NB_env = -1;
   if (NB_env < 0) { const char* e = getenv("LLACUDA_CHOL_NB"); NB_env = e ? atoi(e) : 0; }
   const int64_t NB = NB_env > 0 ? NB_env : (n >= 12288 ? 1024 : 512);
-  if (n <= 2 * NB) return potrf_rec(n, A, lda, 0, uinv, info, s1);
+  const RangeReadyHook* ready = range_ready_hook();   // rows [lo, hi) of the upper triangle
+  if (n <= 2 * NB) {
+    if (ready) LLA_TRY(ready->fn(ready->user, 0, n, s1));
+    return potrf_rec(n, A, lda, 0, uinv, info, s1);
+  }
   cudaStream_t s2 = getenv("LLACUDA_NO_LOOKAHEAD") ? s1 : c->aux;
   cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2], ev_diag = c->ev[3];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
@@ -106,6 +110,7 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     double* uk = uinv + (k / IB) * IB * IB;
     // ---- panel k on s2: the diagonal block needs only part (a1) of the previous update, the block row also (a2)
     trace_mark(s2, "chol.panel>", k, kb);
+    if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
     LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, s2));
     trace_mark(s2, "chol.trsm>", k, n2);
     if (rest_pending) LLA_CUDA(cudaStreamWaitEvent(s2, ev_row, 0));
@@ -120,6 +125,7 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     double* Anext = Arow + kb;                   // A[k+kb, k+kb]
     // (a1) the next diagonal block, (a2) the rest of the next panel's block row: rows [k+kb, k+kb+kb_next), columns [k+kb, n)
     trace_mark(s1, "chol.updA>", k, n2);
+    if (ready && k == 0) LLA_TRY(ready->fn(ready->user, kb, kb + kb_next, s1));
     LLA_TRY(dgemm_dev(1, 0, kb_next, kb_next, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, s1, info));
     LLA_CUDA(cudaEventRecord(ev_diag, s1));
     LLA_CUDA(cudaStreamWaitEvent(s2, ev_diag, 0));
@@ -138,6 +144,16 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
       static int64_t ks_env = -1;
       if (ks_env < 0) { const char* e = getenv("LLACUDA_CHOL_KSPLIT"); ks_env = e ? atoi(e) : 0; }
       const int64_t ks = ks_env > 0 ? ks_env : kb;
+      if (ready && k == 0) {
+        // first step: the update is separable by block row, so each block row starts as soon as it is on the device
+        const int64_t t0 = kb + kb_next;                     // first row / column of this part of the trailing matrix
+        for (int64_t r0 = t0; r0 < n; r0 += READY_BLOCK) {
+          const int64_t r1 = r0 + READY_BLOCK < n ? r0 + READY_BLOCK : n;
+          LLA_TRY(ready->fn(ready->user, r0, r1, s1));
+          const double* P = Arow + (r0 - kb) * lda;          // U(k, r0:)
+          LLA_TRY(dgemm_dev(1, 0, r1 - r0, n - r0, kb, -1.0, P, lda, P, lda, 1.0, A + r0 + r0 * lda, lda, TRI_UPPER, s1, info));
+        }
+      } else
       for (int64_t kk = 0; kk < kb; kk += ks) {
         const int64_t kw = (kb - kk) < ks ? (kb - kk) : ks;
         const double* P = Arow + kk + kb_next * lda;

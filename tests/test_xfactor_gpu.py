@@ -48,8 +48,10 @@ def test_lu_vs_oracle(dt, shape):
         assert np.array_equal(f.ipiv_internal, r1.ipiv_internal), np.flatnonzero(f.ipiv_internal != r1.ipiv_internal)[:5]
         assert np.max(np.abs(f.lu - r1.lu)) <= 100 * max(shape) * eps_of(dt) * np.abs(r1.lu).max()
     # reconstruction P A = L U (lu-random-test, reference tests/linear-algebra.lisp:109-115) holds in any case
-    p = L.ipiv(f.ipiv_internal)
     m, n = shape
+    p = np.arange(m)
+    for i, pi in enumerate(f.ipiv_internal):             # LAPACK's swap sequence replayed on the m row indices
+        p[i], p[pi - 1] = p[pi - 1], p[i]
     k = min(m, n)
     lo = np.tril(f.lu.astype(np.complex128), -1)[:, :k] + np.eye(m, k)
     up = np.triu(f.lu.astype(np.complex128))[:k, :]
