@@ -128,6 +128,14 @@ int llacuda_dgesv_batched_dev(int n, int nrhs, int64_t batch, double* A, int64_t
 int llacuda_dtranspose_dev(int64_t rows, int64_t cols, const double* in, int64_t ldin, double* out,
                            int64_t ldout);
 
+/* convert (+ transpose) on the device: the replacement of copy-array-to-memory / transpose-matrix-to-memory with their
+ * element-wise COERCE (reference src/foreign-memory.lisp:168-255).  Type codes are LLA's (src/types.lisp:22-26: 0 single,
+ * 1 double, 2 complex single, 3 complex double) plus 4 = int32 and 5 = int64 sources (integer arrays classify as double,
+ * src/types.lisp:69-80).  in: rows x cols column-major (ldin); out[c + r ldout] when transpose, out[r + c ldout]
+ * otherwise.  A complex source with a real destination is refused, as the reference does. */
+int llacuda_convert_dev(int in_type, int out_type, int transpose, int64_t rows, int64_t cols, const void* in, int64_t ldin,
+                        void* out, int64_t ldout);
+
 /* Integer type of the Fortran symbols: 32-bit, or 64-bit when the library is built with -DLLACUDA_ILP64
  * (lla_b200/libllacuda64.so) for an LLA compiled with :int64 (reference src/types.lisp:7-8). */
 #ifdef LLACUDA_ILP64

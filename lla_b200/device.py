@@ -95,6 +95,17 @@ def zgemm(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
     _lib.check(f(opa.encode(), opb.encode(), m, n, k, al, A, lda, B, ldb, be, C, ldc), "zgemm_dev")
 
 
+_TYPE_CODE = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3, "int32": 4, "int64": 5}
+
+
+def convert(in_dtype, out_dtype, transpose, rows, cols, src, ldin, dst, ldout):
+    """llacuda_convert_dev: element-wise coercion (+ transpose) on the device, the replacement of LLA's
+    copy-array-to-memory / transpose-matrix-to-memory (reference src/foreign-memory.lisp:168-255)."""
+    f = _sig("llacuda_convert_dev", [ctypes.c_int, ctypes.c_int, ctypes.c_int, _i64, _i64, _vp, _i64, _vp, _i64])
+    _lib.check(f(_TYPE_CODE[str(in_dtype)], _TYPE_CODE[str(out_dtype)], 1 if transpose else 0, rows, cols, src, ldin, dst, ldout),
+               "convert_dev")
+
+
 def dgesv_batched(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu=0):
     f = _sig("llacuda_dgesv_batched_dev", [ctypes.c_int, ctypes.c_int, _i64, _vp, _i64, _ip, _vp, _i64, _ip, ctypes.c_int])
     _lib.check(f(n, nrhs, batch, A, strideA, ipiv, B, strideB, info, keep_lu), "dgesv_batched_dev")

@@ -72,6 +72,47 @@ def common_float_type(*arrays) -> int:
 
 
 # ------------------------------------------------------------------ marshalling (L3/L4)
+# ------------------------------------------------------------------ efficiency warnings (reference src/conditions.lisp:49-74)
+class LlaEfficiencyWarning(UserWarning):
+    """lla-efficiency-warning"""
+
+
+class LlaEfficiencyWarningArrayType(LlaEfficiencyWarning):
+    """lla-efficiency-warning-array-type: an array without a specialised element type had to be checked elementwise."""
+
+
+class LlaEfficiencyWarningArrayConversion(LlaEfficiencyWarning):
+    """lla-efficiency-warning-array-conversion: an array had to be copied / converted to the call's element type --
+    with the device back end that also means its upload could not be shared with the caller's buffer."""
+
+
+# the toggles of src/conditions.lisp:52-66 (off by default, as in the reference)
+efficiency_warning_array_type = False
+efficiency_warning_array_conversion = False
+# below this matrix order a call stays on the host LAPACK in the Lisp glue (lisp/llacuda-glue.lisp *llacuda-min-dimension*,
+# SURVEY.md section 5 :cuda-min-n): the PCIe round trip costs more than the host BLAS call.  The mirror reports it.
+min_dimension = 256
+
+
+def device_worthwhile(*dims) -> bool:
+    """True when every given dimension reaches `min_dimension` (the Lisp glue routes smaller calls to the host library)."""
+    return all(int(d) >= min_dimension for d in dims)
+
+
+def _efficiency_warning_type(a):
+    if efficiency_warning_array_type:
+        import warnings
+        warnings.warn(f"Efficiency warning: had to check a {type(a).__name__} of dtype {getattr(a, 'dtype', None)} elementwise.",
+                      LlaEfficiencyWarningArrayType, stacklevel=3)
+
+
+def _efficiency_warning_conversion(a, dtype):
+    if efficiency_warning_array_conversion:
+        import warnings
+        warnings.warn(f"Efficiency warning: array of dtype {a.dtype} had to be converted to {np.dtype(dtype)} before the upload.",
+                      LlaEfficiencyWarningArrayConversion, stacklevel=3)
+
+
 def _as_memory(a, tcode) -> np.ndarray:
     """share when the array already has the target element type and is a simple (contiguous)
     array, else element-wise coercing copy (src/pinned-array.lisp:124-128, src/foreign-memory.lisp:168-182)."""
@@ -80,6 +121,10 @@ def _as_memory(a, tcode) -> np.ndarray:
         raise TypeError("cannot coerce a complex array to a real type")
     if a.dtype == _DTYPES[tcode] and a.flags.c_contiguous:
         return a
+    if a.dtype == object:
+        _efficiency_warning_type(a)
+    if a.dtype != _DTYPES[tcode]:
+        _efficiency_warning_conversion(a, _DTYPES[tcode])
     return np.array(a, dtype=_DTYPES[tcode], order="C", copy=True)
 
 
@@ -88,6 +133,10 @@ def _transposed_to_memory(a, tcode) -> np.ndarray:
     a = np.asarray(a)
     if np.iscomplexobj(a) and tcode in (SINGLE, DOUBLE):
         raise TypeError("cannot coerce a complex array to a real type")
+    if a.dtype == object:
+        _efficiency_warning_type(a)
+    if a.dtype != _DTYPES[tcode]:
+        _efficiency_warning_conversion(a, _DTYPES[tcode])
     if a.ndim == 1:
         return np.array(a, dtype=_DTYPES[tcode], order="C", copy=True)
     return np.array(a.T, dtype=_DTYPES[tcode], order="C", copy=True)
@@ -501,14 +550,22 @@ def _dev():
 
 
 def _upload_colmajor(a):
-    """Row-major (a0, a1) float64 array -> device buffer holding the column-major a0 x a1 matrix (ld = a0)."""
+    """Row-major (a0, a1) array of any supported element type -> device buffer holding the column-major a0 x a1 double
+    matrix (ld = a0).  The raw bytes travel as they are; coercion to double and the transpose happen in one device
+    kernel (llacuda_convert_dev) instead of LLA's element-wise transpose-matrix-to-memory (src/foreign-memory.lisp:211-230)."""
     D = _dev()
-    a = np.ascontiguousarray(a, dtype=np.float64)
+    a = np.asarray(a)
+    if str(a.dtype) not in ("float32", "float64", "int32", "int64"):
+        _efficiency_warning_conversion(a, np.float64)
+        a = a.astype(np.float64)            # exotic element types (object arrays, small ints, bools): host walk, as the reference
+    elif a.dtype != np.float64:
+        _efficiency_warning_conversion(a, np.float64)
+    a = np.ascontiguousarray(a)
     a0, a1 = a.shape
-    raw, cm = _DevBuf(a.nbytes), _DevBuf(a.nbytes)
+    raw, cm = _DevBuf(a.nbytes), _DevBuf(a0 * a1 * 8)
     _lib.check(_lib.lib().llacuda_memcpy_h2d(raw.p, _ptr(a), ctypes.c_size_t(a.nbytes)), "h2d")
-    # the row-major bytes are the column-major image of a^T (a1 x a0, ld = a1): transpose it on the device
-    D.dtranspose(a1, a0, raw.p, a1, cm.p, a0)
+    # the row-major bytes are the column-major image of a^T (a1 x a0, ld = a1): convert + transpose it on the device
+    D.convert(a.dtype, np.dtype(np.float64), True, a1, a0, raw.p, a1, cm.p, a0)
     return cm
 
 
@@ -590,9 +647,16 @@ def cholesky_device(a) -> DeviceCholesky:
     if a0 != a1:
         raise LlaIncompatibleDimensions()
     D = _dev()
-    a = a.astype(np.float64, copy=False)
-    d_u, d_info = _DevBuf(a.nbytes), _DevBuf(4)
-    _lib.check(_lib.lib().llacuda_memcpy_h2d(d_u.p, _ptr(a), ctypes.c_size_t(a.nbytes)), "h2d")
+    if str(a.dtype) in ("float32", "int32", "int64"):       # classifies as double (integer arrays): coerce on the device
+        _efficiency_warning_conversion(a, np.float64)
+        raw, d_u, d_info = _DevBuf(a.nbytes), _DevBuf(a0 * a1 * 8), _DevBuf(4)
+        _lib.check(_lib.lib().llacuda_memcpy_h2d(raw.p, _ptr(a), ctypes.c_size_t(a.nbytes)), "h2d")
+        D.convert(a.dtype, np.dtype(np.float64), False, a1, a0, raw.p, a1, d_u.p, a1)
+        a = None
+    else:
+        a = a.astype(np.float64, copy=False)
+        d_u, d_info = _DevBuf(a.nbytes), _DevBuf(4)
+        _lib.check(_lib.lib().llacuda_memcpy_h2d(d_u.p, _ptr(a), ctypes.c_size_t(a.nbytes)), "h2d")
     D.dpotrf("U", a0, d_u.p, a0, d_info.p)
     _device_info(d_info, LapackFailure)
     return DeviceCholesky(a0, d_u)

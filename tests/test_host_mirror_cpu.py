@@ -58,3 +58,32 @@ def test_wrappers_and_ipiv_postprocessing():
     a = np.array([[1.0, 2.0], [8.0, 7.0]])                    # P A = L U with P from ipiv (tests/linear-algebra.lisp:114)
     fo = O.lu(a, O.netlib())
     assert np.allclose(a[O.ipiv(fo.ipiv_internal)], O.lu_l(fo) @ O.lu_u(fo))
+
+
+def test_efficiency_warnings_follow_the_reference_toggles():
+    """reference src/conditions.lisp:49-74: off by default, one warning class per toggle."""
+    import warnings
+    from lla_b200 import lla as L
+    a = np.arange(6).reshape(2, 3)                      # integer array: classifies as double, needs a converting copy
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        L._transposed_to_memory(a, L.DOUBLE)            # toggles off: silent
+    L.efficiency_warning_array_conversion = True
+    L.efficiency_warning_array_type = True
+    try:
+        with pytest.warns(L.LlaEfficiencyWarningArrayConversion):
+            L._transposed_to_memory(a, L.DOUBLE)
+        with pytest.warns(L.LlaEfficiencyWarningArrayType):
+            L._as_memory(np.array([[1, 2.5]], dtype=object), L.DOUBLE)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            L._as_memory(np.ones((2, 2)), L.DOUBLE)     # shared as it is: nothing to warn about
+    finally:
+        L.efficiency_warning_array_conversion = False
+        L.efficiency_warning_array_type = False
+    assert issubclass(L.LlaEfficiencyWarningArrayType, L.LlaEfficiencyWarning)
+
+
+def test_min_dimension_threshold():
+    from lla_b200 import lla as L
+    assert L.device_worthwhile(4096, 4096) and not L.device_worthwhile(4096, 8)
