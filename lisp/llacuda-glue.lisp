@@ -27,13 +27,38 @@
 (defparameter *llacuda-min-dimension* (query-configuration :llacuda-min-n 256)
   "Below this matrix order the PCIe round trip costs more than host BLAS; calls stay on the host.")
 
+(defparameter *llacuda-gpus* (query-configuration :llacuda-gpus 1)
+  "Number of GPUs one call is partitioned over (the multi-GPU engine inside libllacuda.so: one process, one host
+thread per GPU, NCCL panel broadcasts).  > 1 routes the hot-path routines of order >= 8192 to llacuda_pd<name>.")
+
 (defun llacuda-load ()
   (cffi:load-foreign-library *llacuda-library*)
   (setf *llacuda-enabled*
         (zerop (cffi:foreign-funcall "llacuda_init" :int)))
   (unless *llacuda-enabled*
     (warn "llacuda: ~A" (cffi:foreign-funcall "llacuda_last_error" :string)))
+  (when *llacuda-enabled*
+    ;; BLAS-style entry points: record the failure and return (LLACUDA-CHECK-BLAS signals it) instead of the
+    ;; XERBLA-style stop of the process
+    (cffi:foreign-funcall "llacuda_set_error_mode" :int 1 :void)
+    (when (> *llacuda-gpus* 1)
+      (unless (zerop (cffi:foreign-funcall "llacuda_dist_init_all" :int *llacuda-gpus* :int 0 :int 0 :int))
+        (warn "llacuda: multi-GPU engine unavailable: ~A" (cffi:foreign-funcall "llacuda_last_error" :string))
+        (setf *llacuda-gpus* 1))))
   *llacuda-enabled*)
+
+(defun llacuda-check-blas ()
+  "Call after every BLAS-CALL that went to the device library: the BLAS symbols have no INFO argument, a device-side
+failure poisons the output with NaN and is reported here (include/llacuda.h, llacuda_set_error_mode)."
+  (unless (zerop (cffi:foreign-funcall "llacuda_last_error_code" :int))
+    (let ((message (cffi:foreign-funcall "llacuda_last_error" :string)))
+      (cffi:foreign-funcall "llacuda_clear_error" :void)
+      (error 'llacuda-device-error :info -1 :message message))))
+
+(defun llacuda-worthwhile-p (&rest dimensions)
+  "The size threshold of SURVEY.md section 5 (:cuda-min-n): below *LLACUDA-MIN-DIMENSION* the PCIe round trip costs
+more than the host BLAS call, so the name generator keeps the host symbol."
+  (and *llacuda-enabled* (every (lambda (d) (>= d *llacuda-min-dimension*)) dimensions)))
 
 ;;;; --- fortran-call.lisp: re-point the name generator for the hot-path routines ----------------
 ;;; reference: src/fortran-call.lisp:405-416 builds "dgemm_" from type letter + name; the ECASE of
@@ -42,9 +67,9 @@
 
 (defparameter *llacuda-routines*
   '(("D" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs" "syrk" "posv" "trsm" "getri" "potri" "trtri"))
-    ("S" . ("gemm"))
-    ("C" . ("gemm"))
-    ("Z" . ("gemm")))
+    ("S" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs" "syrk" "posv"))
+    ("C" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs" "herk" "posv"))
+    ("Z" . ("gemm" "getrf" "getrs" "gesv" "potrf" "potrs" "herk" "posv")))
   "Routines libllacuda.so exports as llacuda_<letter><name> with the Fortran signature.")
 
 (defun llacuda-routine-p (letter name)
@@ -64,6 +89,50 @@ routines the device library implements.  Same argument list, same void return, s
     (if (llacuda-routine-p letter name)
         (format nil "llacuda_~(~A~A~)" letter name)
         (format nil "~(~A~A_~)" letter name))))
+
+;;;; --- fortran-call.lisp: the size threshold and the multi-GPU entry points, decided at run time --------
+;;; BLAS-LAPACK-FUNCTION-NAME runs at macroexpansion time and cannot see the dimensions of a call, so the threshold
+;;; lives in the call form: the generated ECASE branch becomes a run-time choice between the device symbol, the
+;;; multi-GPU symbol (llacuda_pd<name>: same argument list) and the host symbol.  *LLACUDA-CALL-DIMENSION* is bound by
+;;; the hot-path methods (mm, lu, solve, cholesky) around their BLAS-CALL / LAPACK-CALL to the smallest matrix
+;;; dimension of the call; unbound (any other caller) means "host".  The library itself has no CPU fallback: the
+;;; fallback below is the reference's own host LAPACK, loaded next to libllacuda.so.  (Written blind, see the header.)
+
+(defvar *llacuda-call-dimension* nil)
+
+(defparameter *llacuda-multi-gpu-routines* '("gemm" "getrf" "gesv" "potrf" "potrs" "posv")
+  "D (and Z for gemm) routines that libllacuda.so also exports as llacuda_pd<name> / llacuda_pz<name>.")
+
+(defun llacuda-names (type name)
+  "Device, multi-GPU (or NIL) and host symbol for TYPE / NAME."
+  (let+ (((real-name &optional (complex-name name)) (ensure-list name))
+         (letter (switch (type) (+single+ "s") (+double+ "d") (+complex-single+ "c") (+complex-double+ "z")))
+         (name (if (complex? type) complex-name real-name))
+         (host (format nil "~A~A_" letter name)))
+    (values (when (llacuda-routine-p letter name) (format nil "llacuda_~A~A" letter name))
+            (when (and (member name *llacuda-multi-gpu-routines* :test #'string-equal)
+                       (or (string= letter "d") (and (string= letter "z") (string-equal name "gemm"))))
+              (format nil "llacuda_p~A~A" letter name))
+            host)))
+
+(defun blas-lapack-call-form (type-var name arguments &optional (return-types :void))
+  "As the reference (src/fortran-call.lisp:428-439), with a run-time choice of the library per branch."
+  (let ((arguments (arguments-for-cffi arguments)))
+    `(ecase ,type-var
+       ,@(loop for type in +float-types+
+               for return-type in (blas-return-types return-types)
+               collect
+               (multiple-value-bind (device multi host) (llacuda-names type name)
+                 `(,type
+                   (cond
+                     ,@(when multi
+                         `(((and *llacuda-call-dimension* (> *llacuda-gpus* 1) (>= *llacuda-call-dimension* 8192))
+                            (cffi:foreign-funcall ,multi ,@arguments ,return-type))))
+                     ,@(when device
+                         `(((and *llacuda-call-dimension* (llacuda-worthwhile-p *llacuda-call-dimension*))
+                            (prog1 (cffi:foreign-funcall ,device ,@arguments ,return-type)
+                              (llacuda-check-blas)))))
+                     (t (cffi:foreign-funcall ,host ,@arguments ,return-type)))))))))
 
 ;;;; --- conditions: device failures are NOT LAPACK INFO codes -----------------------------------
 ;;; reference: src/fortran-call.lisp:336-347 maps INFO<0 to lapack-invalid-argument.  libllacuda

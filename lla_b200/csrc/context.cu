@@ -8,6 +8,7 @@
 #include "../../include/llacuda.h"
 
 #include <atomic>
+#include <cuda.h>
 #include <vector>
 #include <mutex>
 #include <cstdio>
@@ -104,6 +105,46 @@ Context* ctx() {
   return c;
 }
 
+// ---- SM partition (green contexts), one per device
+static SmPartition g_part[MAX_DEV];
+const SmPartition* sm_partition() {
+  const int dev = cur_dev();
+  if (dev < 0 || dev >= MAX_DEV || !ctx()) return nullptr;
+  SmPartition& P = g_part[dev];
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (P.tried) return P.ok ? &P : nullptr;
+  P.tried = true;
+  if (getenv("LLACUDA_NO_PARTITION")) return nullptr;
+  int want = 24;   // 3 panel CTAs of 128 rows per SM: LU panels up to 9216 rows fit (measured: profiles/r02_sm_partition.md)
+  if (const char* e = getenv("LLACUDA_PANEL_SMS")) want = atoi(e);
+  if (want < 8) return nullptr;
+  CUdevice cudev;
+  CUdevResource all, grp, rem;
+  unsigned int ngroups = 1;
+  CUdevResourceDesc dp = nullptr, dg = nullptr;
+  CUgreenCtx gp = nullptr, gg = nullptr;
+  CUstream sp = nullptr, sg = nullptr, sg2 = nullptr;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  bool ok = cuDeviceGet(&cudev, dev) == CUDA_SUCCESS &&
+            cuDeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+            cuDevSmResourceSplitByCount(&grp, &ngroups, &all, &rem, 0, (unsigned)want) == CUDA_SUCCESS && ngroups == 1 &&
+            rem.sm.smCount >= 64 &&
+            cuDevResourceGenerateDesc(&dp, &grp, 1) == CUDA_SUCCESS && cuDevResourceGenerateDesc(&dg, &rem, 1) == CUDA_SUCCESS &&
+            cuGreenCtxCreate(&gp, dp, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+            cuGreenCtxCreate(&gg, dg, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+            cuGreenCtxStreamCreate(&sp, gp, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
+            cuGreenCtxStreamCreate(&sg, gg, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS &&
+            cuGreenCtxStreamCreate(&sg2, gg, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS;
+  cudaGetLastError();
+  if (!ok) return nullptr;
+  P.panel = (cudaStream_t)sp; P.bulk = (cudaStream_t)sg; P.bulk2 = (cudaStream_t)sg2;
+  P.sm_panel = (int)grp.sm.smCount; P.sm_bulk = (int)rem.sm.smCount;
+  P.ok = true;
+  if (getenv("LLACUDA_TRACE")) fprintf(stderr, "llacuda: SM partition %d (panel chain) + %d (trailing update)\n", P.sm_panel, P.sm_bulk);
+  return &P;
+}
+
 void drain_streams() {
   const int dev = cur_dev();
   if (dev < 0 || dev >= MAX_DEV) return;
@@ -113,6 +154,11 @@ void drain_streams() {
   cudaStreamSynchronize(c->aux);
   cudaStreamSynchronize(c->h2d);
   cudaStreamSynchronize(c->d2h);
+  if (g_part[dev].ok) {
+    cudaStreamSynchronize(g_part[dev].panel);
+    cudaStreamSynchronize(g_part[dev].bulk);
+    cudaStreamSynchronize(g_part[dev].bulk2);
+  }
   cudaGetLastError();
 }
 

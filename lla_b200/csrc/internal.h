@@ -62,6 +62,20 @@ struct Context {
   // timing of the last host-pointer call (ms): [0]=h2d [1]=compute [2]=d2h [3]=total
   float last_ms[4] = {};
 };
+// Spatial split of the SMs (CUDA green contexts) for the chain-bound phase of the blocked factorisations: the panel chain
+// (dozens of short dependent kernels per block step) gets `sm_panel` SMs of its own and the trailing update runs on the
+// rest, so a panel kernel never queues behind 75-150 us GEMM CTAs (measured: panels take 2-3x longer under a concurrent
+// update, profiles/r01b_trace_*.log).  Streams created in a green context only ever run on its SMs.  Optional: when
+// the driver refuses (or LLACUDA_NO_PARTITION is set) the drivers keep their priority streams.
+struct SmPartition {
+  bool tried = false, ok = false;
+  cudaStream_t panel = nullptr;    // on the small partition, high priority
+  cudaStream_t bulk = nullptr;     // on the large partition
+  cudaStream_t bulk2 = nullptr;    // second stream on the large partition, high priority (block-row solves; interchanges of finished columns)
+  int sm_panel = 0, sm_bulk = 0;
+};
+const SmPartition* sm_partition();   // of the current device; nullptr when unavailable
+
 // Lazily initialised, one per device: the context of the calling thread's current device.  The classic entry
 // points run on whatever device is current when they are first called (llacuda_set_device); the multi-GPU engine
 // (dist.cu) drives one thread per device, each of which sees its own context here.

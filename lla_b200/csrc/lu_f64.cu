@@ -491,6 +491,7 @@ struct LuCtx {
   double* linv;    // inverses of the 128 x 128 diagonal blocks of L (unit lower), block b at b*IB*IB
   int64_t swap_c0, swap_c1;  // columns that receive a leaf's interchanges right after the leaf
   cudaStream_t st;
+  int per_sm = 1;            // co-resident panel CTAs per SM (occupancy of the leaf kernel)
 };
 
 static std::atomic<unsigned> g_panel_epoch{1};
@@ -635,9 +636,33 @@ static int lu_blocked(LuCtx L) {
   cudaEvent_t ev_start = c->ev[3], ev_panel = c->ev[4], ev_a = c->ev[5], ev_b = c->ev[6], ev_left = c->ev[7];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
   LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+  // Chain-bound phase: the panel chain (cooperative leaves, interchanges, small solves and products) moves to its own SM
+  // partition, the trailing update to the rest.  Under a concurrent update on shared SMs a panel takes 2-3x as long as
+  // alone (profiles/r01b_trace_dgetrf_16384_leaves.log: leaves 155 us against 83), and from the step where the update is
+  // shorter than the panel that is the critical path.  The cooperative leaf must fit the partition: G <= per_sm * SMs.
+  static int64_t part_m = -1;
+  if (part_m < 0) { const char* e = getenv("LLACUDA_LU_PART_M"); part_m = e ? atol(e) : 8192; }
+  const SmPartition* part = part_m > 0 ? sm_partition() : nullptr;
+  bool part_on = false;
   bool have_b = false;
   for (int64_t k = 0; k < mn; k += NB) {
     const int64_t kb = (mn - k) < NB ? (mn - k) : NB;
+    if (part && !part_on && k > 0 && (L.M - k) <= part_m &&
+        (L.M - k + panel_rows() - 1) / panel_rows() <= (int64_t)L.per_sm * part->sm_panel) {
+      // the update streams of the partition follow everything queued so far; the panel stream only what panel k needs
+      // (the previous panel and the update of its own columns), so the switch costs no look-ahead
+      cudaEvent_t j1 = c->ev[0], j2 = c->ev[1], j3 = c->ev[2];
+      LLA_CUDA(cudaEventRecord(j1, s1));
+      LLA_CUDA(cudaEventRecord(j2, s2));
+      LLA_CUDA(cudaEventRecord(j3, s3));
+      for (cudaStream_t t : {part->bulk, part->bulk2})
+        for (cudaEvent_t e : {j1, j2, j3}) LLA_CUDA(cudaStreamWaitEvent(t, e, 0));
+      LLA_CUDA(cudaStreamWaitEvent(part->panel, j2, 0));
+      LLA_CUDA(cudaStreamWaitEvent(part->panel, ev_a, 0));
+      s1 = part->bulk; s2 = part->panel; s3 = part->bulk2;
+      part_on = true;
+      trace_mark(s1, "lu.partition", k, part->sm_panel);
+    }
     // ---- panel k on s2
     LuCtx P = L;
     P.st = s2; P.swap_c0 = k; P.swap_c1 = k + kb;
@@ -688,6 +713,10 @@ static int lu_blocked(LuCtx L) {
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   if (mn > NB) LLA_CUDA(cudaStreamWaitEvent(s1, ev_left, 0));
+  if (part_on) {   // back to the caller's stream
+    LLA_CUDA(cudaEventRecord(ev_start, s1));
+    LLA_CUDA(cudaStreamWaitEvent(L.st, ev_start, 0));
+  }
   return 0;
 }
 
@@ -723,6 +752,7 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   LuCtx L;
   L.A = A; L.lda = lda; L.M = m; L.N = n; L.ipiv = ipiv; L.info = info_dev; L.st = st;
   L.swap_c0 = 0; L.swap_c1 = n;
+  L.per_sm = per_sm;
   L.hdrs = (PanelHdr*)ar.take(sizeof(PanelHdr) * 2 * maxG);
   L.rows = (PanelRow*)ar.take(sizeof(PanelRow) * 2 * maxG);
   L.rowj = (PanelRow*)ar.take(sizeof(PanelRow) * 2);

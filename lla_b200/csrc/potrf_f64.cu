@@ -98,9 +98,17 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     return potrf_rec(n, A, lda, 0, uinv, info, s1);
   }
   cudaStream_t s2 = getenv("LLACUDA_NO_LOOKAHEAD") ? s1 : c->aux;
-  cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2], ev_diag = c->ev[3];
+  cudaStream_t s0 = s1;   // the caller's stream
+  cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2], ev_diag = c->ev[3], ev_pot = c->ev[4];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
   LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+  // Chain-bound phase (the update of a step is shorter than the panel): the panel chain moves to its own SM partition, the
+  // updates and the block-row solve to the rest, so that no kernel of the chain waits for a GEMM CTA to leave an SM.
+  static int64_t part_n = -1;
+  if (part_n < 0) { const char* e = getenv("LLACUDA_CHOL_PART_N"); part_n = e ? atol(e) : 8192; }
+  const SmPartition* part = (part_n > 0 && s2 != s1) ? sm_partition() : nullptr;
+  bool part_on = false;
+  cudaStream_t st_trsm = s2;
   bool rest_pending = false;  // part (a2) of the previous step: the block row right of the next diagonal block
   for (int64_t k = 0; k < n; k += NB) {
     const int64_t kb = (n - k) < NB ? (n - k) : NB;
@@ -108,16 +116,35 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     double* Akk = A + k + k * lda;
     double* Arow = Akk + kb * lda;             // block row right of the diagonal block
     double* uk = uinv + (k / IB) * IB * IB;
+    if (part && !part_on && k > 0 && (n - k) <= part_n) {
+      // the update streams of the partition follow everything queued so far; the panel stream only what panel k needs
+      // (the previous panel and the update of its diagonal block), so the switch costs no look-ahead
+      LLA_CUDA(cudaEventRecord(ev_start, s1));
+      LLA_CUDA(cudaEventRecord(ev_pot, s2));
+      for (cudaStream_t t : {part->bulk, part->bulk2}) {
+        LLA_CUDA(cudaStreamWaitEvent(t, ev_start, 0));
+        LLA_CUDA(cudaStreamWaitEvent(t, ev_pot, 0));
+      }
+      LLA_CUDA(cudaStreamWaitEvent(part->panel, ev_pot, 0));
+      LLA_CUDA(cudaStreamWaitEvent(part->panel, ev_diag, 0));
+      s1 = part->bulk; s2 = part->panel; st_trsm = part->bulk2;
+      part_on = true;
+      trace_mark(s1, "chol.partition", k, part->sm_panel);
+    }
     // ---- panel k on s2: the diagonal block needs only part (a1) of the previous update, the block row also (a2)
     trace_mark(s2, "chol.panel>", k, kb);
     if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
     LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, s2));
     trace_mark(s2, "chol.trsm>", k, n2);
-    if (rest_pending) LLA_CUDA(cudaStreamWaitEvent(s2, ev_row, 0));
-    if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, s2, info));
-    trace_mark(s2, "chol.panel<", k, kb);
-    LLA_CUDA(cudaEventRecord(ev_panel, s2));
-    if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, s2, nullptr));  // block row k of U is final
+    if (part_on) {   // the block-row solve is a wide GEMM-shaped job: on the large partition
+      LLA_CUDA(cudaEventRecord(ev_pot, s2));
+      LLA_CUDA(cudaStreamWaitEvent(st_trsm, ev_pot, 0));
+    }
+    if (rest_pending) LLA_CUDA(cudaStreamWaitEvent(st_trsm, ev_row, 0));
+    if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, st_trsm, info));
+    trace_mark(st_trsm, "chol.panel<", k, kb);
+    LLA_CUDA(cudaEventRecord(ev_panel, st_trsm));
+    if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, st_trsm, nullptr));  // block row k of U is final
     if (n2 <= 0) break;
     // ---- trailing update of step k on s1
     LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
@@ -164,6 +191,10 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     trace_mark(s1, "chol.updB<", k, n3);
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
+  if (part_on) {   // back to the caller's stream
+    LLA_CUDA(cudaEventRecord(ev_start, s1));
+    LLA_CUDA(cudaStreamWaitEvent(s0, ev_start, 0));
+  }
   return 0;
 }
 
