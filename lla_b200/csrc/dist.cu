@@ -169,7 +169,8 @@ static int rank_resources(Rank& R) {
   int lo = 0, hi = 0;
   LLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   LLA_CUDA(cudaStreamCreateWithPriority(&R.main, cudaStreamNonBlocking, lo));
-  LLA_CUDA(cudaStreamCreateWithPriority(&R.side, cudaStreamNonBlocking, hi));
+  LLA_CUDA(cudaStreamCreateWithPriority(&R.side, cudaStreamNonBlocking, hi + (hi < lo ? 1 : 0)));
+  LLA_CUDA(cudaStreamCreateWithPriority(&R.chain, cudaStreamNonBlocking, hi));
   for (auto& e : R.ev) LLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   LLA_CUDA(cudaMalloc((void**)&R.dflag, 8 * sizeof(int)));
   LLA_CUDA(cudaMemset(R.dflag, 0, 8 * sizeof(int)));
@@ -215,6 +216,7 @@ int finish_info(Rank& R, int* info_out) {
   LLA_CUDA(cudaMemcpyAsync(R.hflag, R.dflag, sizeof(int), cudaMemcpyDeviceToHost, R.main));
   LLA_CUDA(cudaStreamSynchronize(R.main));
   LLA_CUDA(cudaStreamSynchronize(R.side));
+  LLA_CUDA(cudaStreamSynchronize(R.chain));
   if (info_out) *info_out = R.hflag[0];
   return 0;
 }
@@ -351,6 +353,7 @@ int llacuda_dist_finalize(void) {
     }
     if (R.main) cudaStreamDestroy(R.main);
     if (R.side) cudaStreamDestroy(R.side);
+    if (R.chain) cudaStreamDestroy(R.chain);
     for (auto& e : R.ev) if (e) cudaEventDestroy(e);
     if (R.dflag) cudaFree(R.dflag);
     if (R.hflag) cudaFreeHost(R.hflag);

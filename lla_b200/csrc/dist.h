@@ -50,6 +50,7 @@ struct Rank {
   ncclComm_t colc = nullptr;    // the P ranks of my grid column (rank inside = p)
   cudaStream_t main = nullptr;  // trailing updates
   cudaStream_t side = nullptr;  // panels + every collective (one issue order per communicator)
+  cudaStream_t chain = nullptr; // the diagonal chain of the block-column Cholesky (its broadcasts use `world`, the row exchange `rowc`)
   cudaEvent_t ev[24] = {};
   int* dflag = nullptr;         // 8 device ints: [0] INFO accumulator, [1] INFO of the last local factorisation
   int* hflag = nullptr;         // pinned mirror

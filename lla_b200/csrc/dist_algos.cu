@@ -9,6 +9,7 @@
 #include "staging.h"
 #include "../../include/llacuda.h"
 
+#include <cstdlib>
 #include <vector>
 
 namespace llacuda {
@@ -167,6 +168,132 @@ template int summa_rank<cuDoubleComplex>(Rank&, int64_t, int64_t, int64_t, int64
 //      up to the diagonal.  Blocks below the diagonal are scratch, so no masking is needed.
 // Look-ahead: the update of block row k+1 goes first; panel k+1 (kernels and collectives) then runs on `side`
 // under the rest of update k.
+// Block columns (1 x Q, the default grid): every row of a block column is local, and the critical chain of the
+// factorisation is diag(k) -> U(k, k+1) -> diag(k+1).  The diagonal blocks therefore get their updates on a stream of
+// their own ("chain"): as soon as a rank has solved its piece of block row k it subtracts U(k, J)^T U(k, J) from its own
+// diagonal blocks (the one the next step factors first), so the owner of block column k+1 can factor and broadcast
+// diag(k+1) while block row k is still being exchanged and the trailing update of step k runs.  The diagonal broadcasts
+// use the world communicator, the row exchange the row communicator: two communicators progress independently.
+static int pdpotrf_rank_cols(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld) {
+  const NcclApi* nc = nccl();
+  const int Q = R.Q, q = R.q;
+  const int64_t nloc = Np / Q, nblk = Np / nb, nbl = nloc / nb;
+  PoolBuf wcb[2], wrb[2], xchg, dblk[2], tinv[2];
+  for (int i = 0; i < 2; i++) {
+    LLA_TRY(wcb[i].alloc((size_t)nloc * nb * 8));
+    LLA_TRY(wrb[i].alloc((size_t)Np * nb * 8));
+    LLA_TRY(dblk[i].alloc((size_t)nb * nb * 8));
+    LLA_TRY(tinv[i].alloc(tinv_bytes(nb)));
+  }
+  LLA_TRY(xchg.alloc((size_t)Np * nb * 8));
+  int* info_acc = R.dflag;
+  int* info_last = R.dflag + 1;
+  LLA_CUDA(cudaMemsetAsync(R.dflag, 0, 2 * sizeof(int), R.main));
+  cudaEvent_t evD[2] = {R.ev[0], R.ev[1]}, evTrsm[2] = {R.ev[2], R.ev[3]}, evRow[2] = {R.ev[4], R.ev[5]},
+              evUpd[2] = {R.ev[6], R.ev[7]}, evLook = R.ev[8], evStart = R.ev[9], evSyrk = R.ev[10];
+  cudaStream_t sm = R.main, sd = R.side, sc = R.chain;
+  LLA_CUDA(cudaEventRecord(evStart, sm));
+  LLA_CUDA(cudaStreamWaitEvent(sd, evStart, 0));
+  LLA_CUDA(cudaStreamWaitEvent(sc, evStart, 0));
+  // diag(J, J) -= U(k, J)^T U(k, J) for my block columns lj in [a, b)
+  auto syrk = [&](int64_t k, int64_t a, int64_t b) -> int {
+    for (int64_t lj = a; lj < b; lj++) {
+      const int64_t J = lj * Q + q;
+      const double* Ukj = A + k * nb + lj * nb * lld;
+      LLA_TRY(dgemm_dev(1, 0, nb, nb, nb, -1.0, Ukj, lld, Ukj, lld, 1.0, A + J * nb + lj * nb * lld, lld, TRI_UPPER, sc));
+    }
+    return 0;
+  };
+  for (int64_t k = 0; k < nblk; k++) {
+    const int slot = (int)(k & 1);
+    const int qk = (int)(k % Q);
+    double* D = (double*)dblk[slot].p;
+    double* wc = (double*)wcb[slot].p;
+    double* wr = (double*)wrb[slot].p;
+    const int64_t lj0 = blocks_le(k, q, Q);           // my first block column with J > k
+    const int64_t ncols = nloc - lj0 * nb;
+    // ---- chain: factor diag(k), broadcast it, invert its 128-blocks
+    if (q == qk) {
+      double* diag = A + k * nb + (k / Q) * nb * lld;
+      LLA_TRY(dpotrf_dev(true, nb, diag, lld, info_last, sc));
+      lla_info_acc_kernel<<<1, 1, 0, sc>>>(info_acc, info_last, (int)(k * nb));
+      count_launch();
+      LLA_TRY(d2d_2d(D, nb, diag, lld, nb, nb, 8, sc));
+    }
+    LLA_NCCL(nc->Broadcast(D, D, (size_t)nb * nb, ncclDouble, qk, R.world, sc));
+    LLA_TRY(dtrtri_blocks_dev(true, false, nb, D, nb, (double*)tinv[slot].p, sc));
+    LLA_CUDA(cudaEventRecord(evD[slot], sc));
+    // the rest of the previous row's contributions to my diagonal blocks (the nearest one went ahead of this step's factorisation)
+    if (k > 0) {
+      const int64_t a = blocks_le(k, q, Q);            // columns J > k; J == k was applied before diag(k) was factored
+      LLA_TRY(syrk(k - 1, a, nbl));
+    }
+    // ---- side: my piece of block row k, then the exchange of the whole row
+    LLA_CUDA(cudaStreamWaitEvent(sd, evD[slot], 0));
+    if (k > 0) LLA_CUDA(cudaStreamWaitEvent(sd, evLook, 0));
+    if (k >= 2) LLA_CUDA(cudaStreamWaitEvent(sd, evUpd[slot], 0));      // update k-2 has finished with this slot's buffers
+    if (ncols > 0) {
+      double* row = A + k * nb + lj0 * nb * lld;
+      LLA_TRY(dtrsm_left_inv_dev(true, 1, nb, ncols, D, nb, (const double*)tinv[slot].p, row, lld, sd));
+      LLA_CUDA(cudaEventRecord(evTrsm[slot], sd));
+      LLA_TRY(d2d_2d(wc, nb, row, lld, nb, ncols, 8, sd));
+    } else {
+      LLA_CUDA(cudaEventRecord(evTrsm[slot], sd));
+    }
+    // chain again: the contribution of row k to the diagonal block the next step factors, if it is mine
+    LLA_CUDA(cudaStreamWaitEvent(sc, evTrsm[slot], 0));
+    if (k + 1 < nblk && (int)((k + 1) % Q) == q) LLA_TRY(syrk(k, lj0, lj0 + 1));
+    LLA_CUDA(cudaEventRecord(evSyrk, sc));
+    if (k + 1 >= nblk) break;
+    // exchange: every rank contributes U(k, J) for its J > k; everybody needs the whole row as left factors
+    {
+      double* X = (double*)xchg.p;
+      std::vector<int64_t> seg((size_t)Q + 1, 0);
+      for (int qq = 0; qq < Q; qq++) seg[(size_t)qq + 1] = seg[(size_t)qq] + (nbl - blocks_le(k, qq, Q));
+      if (ncols > 0) LLA_TRY(d2d_2d(X + seg[(size_t)q] * nb * nb, nb, wc, nb, nb, ncols, 8, sd));
+      LLA_NCCL(nc->GroupStart());
+      for (int qq = 0; qq < Q; qq++) {
+        const int64_t cnt = seg[(size_t)qq + 1] - seg[(size_t)qq];
+        if (cnt > 0) LLA_NCCL(nc->Broadcast(X + seg[(size_t)qq] * nb * nb, X + seg[(size_t)qq] * nb * nb, (size_t)cnt * nb * nb, ncclDouble, qq, R.rowc, sd));
+      }
+      LLA_NCCL(nc->GroupEnd());
+      std::vector<long long> soff, doff;   // interleave into block order: wr block (I - k - 1) = U(k, I)
+      for (int qq = 0; qq < Q; qq++) {
+        const int64_t l0 = blocks_le(k, qq, Q);
+        for (int64_t lj = l0; lj < nbl; lj++) {
+          soff.push_back((long long)((seg[(size_t)qq] + (lj - l0)) * nb * nb));
+          doff.push_back((long long)((lj * Q + qq - k - 1) * nb * nb));
+        }
+      }
+      LLA_TRY(copy_blocks<double>(X, nb, wr, nb, (int)nb, (int)nb, soff, doff, sd));
+      LLA_CUDA(cudaEventRecord(evRow[slot], sd));
+    }
+    // ---- main: off-diagonal update; block row k+1 first (the next step's solve needs it)
+    LLA_CUDA(cudaStreamWaitEvent(sm, evRow[slot], 0));
+    {
+      const int64_t l1 = blocks_le(k + 1, q, Q);        // my columns J > k+1
+      if (l1 < nbl)   // A(k+1, J) -= U(k, k+1)^T U(k, J)
+        LLA_TRY(dgemm_dev(1, 0, nb, (nbl - l1) * nb, nb, -1.0, wr, nb, wc + (l1 - lj0) * nb * nb, nb, 1.0,
+                          A + (k + 1) * nb + l1 * nb * lld, lld, TRI_FULL, sm));
+      LLA_CUDA(cudaEventRecord(evLook, sm));
+      for (int64_t lj = l1; lj < nbl; lj++) {           // rows I = k+2 .. J-1 of column J
+        const int64_t J = lj * Q + q;
+        const int64_t rows = J - (k + 2);
+        if (rows <= 0) continue;
+        LLA_TRY(dgemm_dev(1, 0, rows * nb, nb, nb, -1.0, wr + nb * nb, nb, wc + (lj - lj0) * nb * nb, nb, 1.0,
+                          A + (k + 2) * nb + lj * nb * lld, lld, TRI_FULL, sm));
+      }
+      LLA_CUDA(cudaEventRecord(evUpd[slot], sm));
+    }
+  }
+  for (cudaStream_t t : {sd, sc}) {
+    LLA_CUDA(cudaEventRecord(evStart, t));
+    LLA_CUDA(cudaStreamWaitEvent(sm, evStart, 0));
+  }
+  LLA_CUDA(cudaStreamSynchronize(sm));   // the pooled buffers are released with this frame
+  return 0;
+}
+
 int pdpotrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld) {
   const NcclApi* nc = nccl();
   const int P = R.P, Q = R.Q, p = R.p, q = R.q;
@@ -174,6 +301,8 @@ int pdpotrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld) {
     set_error(__FILE__, __LINE__, "pdpotrf: the padded order must be a multiple of nb * lcm(P, Q), nb of 128", (int)nb);
     return LLACUDA_ERR_BAD_ARG;
   }
+  static const bool no_fast = getenv("LLACUDA_CHOL_NO_DIAG_CHAIN") != nullptr;
+  if (P == 1 && Q > 1 && !no_fast) return pdpotrf_rank_cols(R, Np, nb, A, lld);
   const int64_t mloc = Np / P, nloc = Np / Q, nblk = Np / nb, mb = mloc / nb, nbl = nloc / nb;
   PoolBuf wcb[2], wrb[2], xchg, dblk, tinv;
   for (int i = 0; i < 2; i++) {
