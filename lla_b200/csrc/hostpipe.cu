@@ -18,7 +18,7 @@ namespace llacuda {
 namespace {
 
 constexpr size_t SLAB_BYTES = size_t(16) << 20;
-constexpr int NSLAB = 4;                       // per direction
+constexpr int NSLAB = 3;                       // per direction and device
 constexpr size_t PIECE_BYTES = size_t(1) << 20;
 
 // ------------------------------------------------------------------ parallel host memcpy
@@ -63,9 +63,9 @@ class CopyPool {
     if (const char* e = getenv("LLACUDA_COPY_THREADS")) n = atoi(e);
     if (n <= 0) {
       unsigned hw = std::thread::hardware_concurrency();
-      n = (int)(hw / 2);
+      n = (int)(hw * 3 / 4);
       if (n < 2) n = 2;
-      if (n > 8) n = 8;
+      if (n > 12) n = 12;
     }
     for (int i = 0; i < n - 1; i++) std::thread([this] { loop(); }).detach();
   }
@@ -261,8 +261,20 @@ class Pipe {
   }
 };
 
-Pipe& up_pipe() { static Pipe* p = new Pipe(true); return *p; }
-Pipe& down_pipe() { static Pipe* p = new Pipe(false); return *p; }
+// one uploader and one downloader per device: the rank threads of the multi-GPU engine stage concurrently
+std::mutex g_pipe_mu;
+Pipe* g_up[MAX_DEV] = {};
+Pipe* g_down[MAX_DEV] = {};
+Pipe& up_pipe(int dev) {
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  if (!g_up[dev]) g_up[dev] = new Pipe(true);
+  return *g_up[dev];
+}
+Pipe& down_pipe(int dev) {
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  if (!g_down[dev]) g_down[dev] = new Pipe(false);
+  return *g_down[dev];
+}
 
 std::shared_ptr<XferState> make_state(bool up, void* dev, size_t dpitch, void* host, size_t hpitch, size_t width,
                                       size_t ncols, cudaEvent_t after) {
@@ -310,7 +322,7 @@ cudaEvent_t Xfer::event() { return s ? s->ev : nullptr; }
 Xfer pipe_upload(void* dev, size_t dpitch, const void* host, size_t hpitch, size_t width, size_t ncols) {
   Xfer x;
   x.s = make_state(true, dev, dpitch, const_cast<void*>(host), hpitch, width, ncols, nullptr);
-  up_pipe().submit(x.s);
+  up_pipe(x.s->dev).submit(x.s);
   return x;
 }
 
@@ -318,7 +330,7 @@ Xfer pipe_download(void* host, size_t hpitch, const void* dev, size_t dpitch, si
                    cudaEvent_t after) {
   Xfer x;
   x.s = make_state(false, const_cast<void*>(dev), dpitch, host, hpitch, width, ncols, after);
-  down_pipe().submit(x.s);
+  down_pipe(x.s->dev).submit(x.s);
   return x;
 }
 
