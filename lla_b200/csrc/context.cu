@@ -118,6 +118,26 @@ const SmPartition* sm_partition() {
   int want = 24;   // 3 panel CTAs of 128 rows per SM: LU panels up to 9216 rows fit (measured: profiles/r02_sm_partition.md)
   if (const char* e = getenv("LLACUDA_PANEL_SMS")) want = atoi(e);
   if (want < 8) return nullptr;
+  // the driver API is resolved at run time (cudaGetDriverEntryPoint): the library must load on a machine without libcuda
+  typedef CUresult (*DevGet)(CUdevice*, int);
+  typedef CUresult (*GetRes)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*Split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*GenDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*GreenCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*GreenStream)(CUstream*, CUgreenCtx, unsigned int, int);
+  auto entry = [](const char* name) -> void* {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return fn;
+  };
+  DevGet dev_get = (DevGet)entry("cuDeviceGet");
+  GetRes get_res = (GetRes)entry("cuDeviceGetDevResource");
+  Split split = (Split)entry("cuDevSmResourceSplitByCount");
+  GenDesc gen_desc = (GenDesc)entry("cuDevResourceGenerateDesc");
+  GreenCreate green_create = (GreenCreate)entry("cuGreenCtxCreate");
+  GreenStream green_stream = (GreenStream)entry("cuGreenCtxStreamCreate");
+  if (!dev_get || !get_res || !split || !gen_desc || !green_create || !green_stream) return nullptr;
   CUdevice cudev;
   CUdevResource all, grp, rem;
   unsigned int ngroups = 1;
@@ -126,16 +146,16 @@ const SmPartition* sm_partition() {
   CUstream sp = nullptr, sg = nullptr, sg2 = nullptr;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  bool ok = cuDeviceGet(&cudev, dev) == CUDA_SUCCESS &&
-            cuDeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
-            cuDevSmResourceSplitByCount(&grp, &ngroups, &all, &rem, 0, (unsigned)want) == CUDA_SUCCESS && ngroups == 1 &&
+  bool ok = dev_get(&cudev, dev) == CUDA_SUCCESS &&
+            get_res(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+            split(&grp, &ngroups, &all, &rem, 0, (unsigned)want) == CUDA_SUCCESS && ngroups == 1 &&
             rem.sm.smCount >= 64 &&
-            cuDevResourceGenerateDesc(&dp, &grp, 1) == CUDA_SUCCESS && cuDevResourceGenerateDesc(&dg, &rem, 1) == CUDA_SUCCESS &&
-            cuGreenCtxCreate(&gp, dp, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
-            cuGreenCtxCreate(&gg, dg, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
-            cuGreenCtxStreamCreate(&sp, gp, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
-            cuGreenCtxStreamCreate(&sg, gg, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS &&
-            cuGreenCtxStreamCreate(&sg2, gg, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS;
+            gen_desc(&dp, &grp, 1) == CUDA_SUCCESS && gen_desc(&dg, &rem, 1) == CUDA_SUCCESS &&
+            green_create(&gp, dp, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+            green_create(&gg, dg, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+            green_stream(&sp, gp, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
+            green_stream(&sg, gg, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS &&
+            green_stream(&sg2, gg, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS;
   cudaGetLastError();
   if (!ok) return nullptr;
   P.panel = (cudaStream_t)sp; P.bulk = (cudaStream_t)sg; P.bulk2 = (cudaStream_t)sg2;
