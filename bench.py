@@ -456,6 +456,37 @@ def batched_leg(rank, world, local_rank):
     return out
 
 
+def sgemm_leg(local_rank):
+    """single precision on tcgen05 (3xTF32, TMA + TMEM): n = 8192, NN, device-resident, rank 0's GPU only"""
+    import torch
+    from lla_b200 import device as D
+    dev = torch.device("cuda", local_rank)
+    D.use_torch_stream()
+    n = 8192
+    g = torch.Generator(device=dev).manual_seed(21)
+    A = torch.rand((n, n), dtype=torch.float32, device=dev, generator=g) - 0.5
+    B = torch.rand((n, n), dtype=torch.float32, device=dev, generator=g) - 0.5
+    C = torch.empty_like(A)
+    times = []
+    for it in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        D.sgemm("N", "N", n, n, n, 1.0, A.data_ptr(), n, B.data_ptr(), n, 0.0, C.data_ptr(), n)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = statistics.mean(times)
+    # C_img = B_img A_img in torch terms (column-major product A B): sampled columns against float64
+    sel = [5, 4097, 8191]
+    ref = (B.double()[sel, :] @ A.double()).float()
+    err = ((C[sel, :] - ref).abs().max() / ref.abs().max()).item()
+    del A, B, C
+    torch.cuda.empty_cache()
+    return {"ms": ms, "tflops": 2.0 * n ** 3 / ms / 1e9, "max_err_over_max_abs": err}
+
+
 def n32768_leg(args, rank, world, local_rank):
     """BASELINE configs[4] and the north_star scaling target: DGEMM / ZGEMM / Cholesky / LU at n = 32768, one run each
     after one warm-up, same engine, same seeded matrices for every N."""
@@ -702,6 +733,20 @@ def main():
             "roofline": {"kernel": "lla_dgesv_batched_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm * world, "unit": "GB/s",
                          "frac": gbs / (hbm * world), "algorithmic_bytes_per_system": 8704,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured) x GPUs; L2 flushed between launches"}}
+        if rank == 0:
+            sg = sgemm_leg(local_rank)
+            bf16 = 1663.5
+            try:
+                bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+            except Exception:
+                pass
+            roof = bf16 / 2 / 3      # dense TF32 = half the measured bf16 rate; three TF32 products per FP32 product
+            secondary["sgemm_8192"] = {
+                "workload": "SGEMM n = 8192 (lla:mm on single-float arrays), one GPU, device-resident",
+                "ms": sg["ms"], "tflops_fp32_equivalent": sg["tflops"], "max_err_over_max_abs": sg["max_err_over_max_abs"],
+                "roofline": {"kernel": "lla_sgemm_tcgen05_kernel (tcgen05.mma kind::tf32 x3, TMA, TMEM)", "bound": "tensor",
+                             "achieved": sg["tflops"], "peak": roof, "unit": "TFLOP/s", "frac": sg["tflops"] / roof,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops (of measured) / 2 (TF32) / 3 (3xTF32 split)"}}
         secondary["n32768"] = n32768_leg(args, rank, world, local_rank)
     # ---- e2e: one process, host buffers
     e2e = None

@@ -87,8 +87,12 @@ int llacuda_dsyrk_like_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, 
                            const double* A, int64_t lda, const double* B, int64_t ldb,
                            double beta, double* C, int64_t ldc, int tri);
 
-/* single precision on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulation in TMEM), TMA-fed:
- * A, B 16-byte aligned with lda, ldb multiples of 4 */
+/* single precision on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulation in TMEM), TMA-fed when A, B are 16-byte
+ * aligned with lda, ldb multiples of 4; any other operand goes to an FP32-FMA tile kernel (same result class as a reference
+ * SGEMM, much slower).  Accuracy of the tcgen05 path (also behind sgemm_ / cgemm_): the hi/lo TF32 split is exact to
+ * ~2^-21 and TMEM accumulation truncates, which leaves a relative bias of about 3e-6 of max|C| on same-sign data (about
+ * 50 FP32 eps; tests/test_gemm_gpu.py bounds it at 4e-6); an infinite operand element yields NaN in its row / column of
+ * the product (inf - inf in the split), where a reference SGEMM would return inf. */
 int llacuda_sgemm_dev(char opa, char opb, int64_t m, int64_t n, int64_t k, float alpha,
                       const float* A, int64_t lda, const float* B, int64_t ldb,
                       float beta, float* C, int64_t ldc);

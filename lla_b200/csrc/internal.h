@@ -146,6 +146,10 @@ int zgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, cuDoubleComplex
 int sgemm_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
               const float* B, int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st);
 
+// FP32-FMA tile kernel (xfactor.cu): any alignment, reference-SGEMM accuracy; the fallback of sgemm_dev for operands TMA cannot take
+int sgemm_simt_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
+                   const float* B, int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st);
+
 // ------------------------------------------------------------------ TRSM (trsm_f64.cu), left side only
 // solves op(T) X = alpha B in place; T is m x m triangular, B is m x n
 int dtrsm_left_dev(bool upper, int op, bool unit, int64_t m, int64_t n,

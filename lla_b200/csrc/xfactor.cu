@@ -168,6 +168,11 @@ int xgemm_dev<C64>(int opa, int opb, int64_t m, int64_t n, int64_t k, C64 alpha,
   return zgemm_dev(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri, st);
 }
 
+int sgemm_simt_dev(int opa, int opb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st) {
+  return xgemm_dev<float>(opa, opb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, TRI_FULL, st, nullptr);
+}
+
 // ------------------------------------------------------------------ LU panel (cooperative, one thread per row)
 constexpr int XW = 32;      // panel width
 constexpr int XR = 256;     // rows per CTA

@@ -271,3 +271,30 @@ def test_dgemm_host_two_dimensional_pipeline():
     assert np.all(np.abs(got - want0) <= tol)
     got = L.gemm(0.7, a, b, 1.3, c.copy())
     assert np.all(np.abs(got - (0.7 * want0 + 1.3 * c)) <= 0.7 * tol + 8 * EPS * 1.3 * np.abs(c))
+
+
+def test_sgemm_dev_takes_unaligned_operands():
+    """llacuda_sgemm_dev with leading dimensions that TMA cannot take (odd lda / ldb, LLA's sloppy arrays): served by the
+    FP32-FMA tile kernel instead of an error."""
+    import ctypes
+    from lla_b200 import _lib, device as D
+    lib = _lib.lib()
+    _lib.init(0)
+    lib.llacuda_reset_stream()
+    rng = np.random.default_rng(3)
+    m, n, k, lda, ldb, ldc = 70, 45, 130, 71, 131, 73
+    a = rng.normal(size=(k, lda)).astype(np.float32)       # column-major m x k with leading dimension lda (image rows = columns)
+    b = rng.normal(size=(n, ldb)).astype(np.float32)
+    c = rng.normal(size=(n, ldc)).astype(np.float32)
+    bufs = []
+    for h in (a, b, c):
+        d = L._DevBuf(h.nbytes)
+        _lib.check(lib.llacuda_memcpy_h2d(d.p, h.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(h.nbytes)), "h2d")
+        bufs.append(d)
+    D.sgemm("N", "N", m, n, k, 1.5, bufs[0].p, lda, bufs[1].p, ldb, 0.5, bufs[2].p, ldc)
+    out = np.empty_like(c)
+    _lib.check(lib.llacuda_memcpy_d2h(out.ctypes.data_as(ctypes.c_void_p), bufs[2].p, ctypes.c_size_t(out.nbytes)), "d2h")
+    am, bm = a[:, :m].T.astype(np.float64), b[:, :k].T.astype(np.float64)
+    ref = 1.5 * (am @ bm) + 0.5 * c[:, :m].T
+    assert np.max(np.abs(out[:, :m].T - ref)) <= 64 * k * np.finfo(np.float32).eps * np.abs(ref).max()
+    assert np.array_equal(out[:, m:], c[:, m:])             # the padding rows of C are untouched
