@@ -98,6 +98,8 @@ Context* ctx() {
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo);
   cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, hi);  // panels ahead of trailing updates
+  cudaStreamCreateWithPriority(&c->aux2, cudaStreamNonBlocking, hi);
+  cudaStreamCreateWithPriority(&c->aux3, cudaStreamNonBlocking, hi);
   cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
   for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -143,7 +145,7 @@ const SmPartition* sm_partition() {
   unsigned int ngroups = 1;
   CUdevResourceDesc dp = nullptr, dg = nullptr;
   CUgreenCtx gp = nullptr, gg = nullptr;
-  CUstream sp = nullptr, sg = nullptr, sg2 = nullptr;
+  CUstream sp = nullptr, sg = nullptr, sg2 = nullptr, sg3 = nullptr;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   bool ok = dev_get(&cudev, dev) == CUDA_SUCCESS &&
@@ -155,10 +157,11 @@ const SmPartition* sm_partition() {
             green_create(&gg, dg, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
             green_stream(&sp, gp, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
             green_stream(&sg, gg, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS &&
-            green_stream(&sg2, gg, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS;
+            green_stream(&sg2, gg, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS &&
+            green_stream(&sg3, gg, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS;
   cudaGetLastError();
   if (!ok) return nullptr;
-  P.panel = (cudaStream_t)sp; P.bulk = (cudaStream_t)sg; P.bulk2 = (cudaStream_t)sg2;
+  P.panel = (cudaStream_t)sp; P.bulk = (cudaStream_t)sg; P.bulk2 = (cudaStream_t)sg2; P.bulk3 = (cudaStream_t)sg3;
   P.sm_panel = (int)grp.sm.smCount; P.sm_bulk = (int)rem.sm.smCount;
   P.ok = true;
   if (getenv("LLACUDA_TRACE")) fprintf(stderr, "llacuda: SM partition %d (panel chain) + %d (trailing update)\n", P.sm_panel, P.sm_bulk);
@@ -172,12 +175,15 @@ void drain_streams() {
   if (!c) return;
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->aux);
+  cudaStreamSynchronize(c->aux2);
+  cudaStreamSynchronize(c->aux3);
   cudaStreamSynchronize(c->h2d);
   cudaStreamSynchronize(c->d2h);
   if (g_part[dev].ok) {
     cudaStreamSynchronize(g_part[dev].panel);
     cudaStreamSynchronize(g_part[dev].bulk);
     cudaStreamSynchronize(g_part[dev].bulk2);
+    cudaStreamSynchronize(g_part[dev].bulk3);
   }
   cudaGetLastError();
 }
@@ -318,6 +324,8 @@ int llacuda_synchronize(void) {
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   LLA_CUDA(cudaStreamSynchronize(c->stream));
   LLA_CUDA(cudaStreamSynchronize(c->aux));
+  LLA_CUDA(cudaStreamSynchronize(c->aux2));
+  LLA_CUDA(cudaStreamSynchronize(c->aux3));
   return 0;
 }
 

@@ -55,9 +55,11 @@ struct Context {
   int sm_count = 0;
   cudaStream_t stream = nullptr;     // main compute stream
   cudaStream_t aux = nullptr;        // panel / look-ahead stream
+  cudaStream_t aux3 = nullptr;       // third high-priority stream: the part of a block row the panel chain needs next
+  cudaStream_t aux2 = nullptr;       // second high-priority stream: block-row solves beside the trailing update
   cudaStream_t h2d = nullptr;        // staging streams
   cudaStream_t d2h = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[12] = {};
   cudaStream_t own_stream = nullptr; // the library's stream while a caller-owned one is adopted (llacuda_set_stream)
   // timing of the last host-pointer call (ms): [0]=h2d [1]=compute [2]=d2h [3]=total
   float last_ms[4] = {};
@@ -72,6 +74,7 @@ struct SmPartition {
   cudaStream_t panel = nullptr;    // on the small partition, high priority
   cudaStream_t bulk = nullptr;     // on the large partition
   cudaStream_t bulk2 = nullptr;    // second stream on the large partition, high priority (block-row solves; interchanges of finished columns)
+  cudaStream_t bulk3 = nullptr;    // third stream on the large partition, high priority (block-row solves beside the update)
   int sm_panel = 0, sm_bulk = 0;
 };
 const SmPartition* sm_partition();   // of the current device; nullptr when unavailable

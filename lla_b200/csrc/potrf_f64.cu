@@ -70,6 +70,21 @@ static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, double* uin
     LLA_CUDA(cudaGetLastError());
     return 0;
   }
+  static int64_t rl_max = -1;   // up to this order: right-looking over the 128-column leaves (3 launches per leaf instead of 4)
+  if (rl_max < 0) { const char* e = getenv("LLACUDA_CHOL_RL_MAX"); rl_max = e ? atol(e) : 1024; }
+  if (n <= rl_max) {
+    for (int64_t j = 0; j < n; j += IB) {
+      const int64_t jb = (n - j) < IB ? (n - j) : IB, rest = n - j - jb;
+      double* Ajj = A + j + j * lda;
+      double* Arow = Ajj + jb * lda;
+      double* uj = uinv + (j / IB) * IB * IB;
+      LLA_TRY(potrf_rec(jb, Ajj, lda, off + j, uj, info, st));
+      if (rest <= 0) break;
+      LLA_TRY(dtrsm_left_inv_dev(true, 1, jb, rest, Ajj, lda, uj, Arow, lda, st, info));
+      LLA_TRY(dgemm_dev(1, 0, rest, rest, jb, -1.0, Arow, lda, Arow, lda, 1.0, Arow + jb, lda, TRI_UPPER, st, info));
+    }
+    return 0;
+  }
   int64_t n1 = ((n / 2 + IB - 1) / IB) * IB;
   int64_t n2 = n - n1;
   double* A12 = A + n1 * lda;
@@ -81,10 +96,39 @@ static int potrf_rec(int64_t n, double* A, int64_t lda, int64_t off, double* uin
   return 0;
 }
 
-// Blocked right-looking driver with one panel of look-ahead.  Step k factors the diagonal block
-// (recursively, down to the shared-memory leaves) and solves for its block row on the high-priority
-// panel stream while the previous step's trailing update is still running on the main stream: the
-// update of step k-1 is split into (a) the block row that panel k needs and (b) everything below.
+// Diagonal block of a blocked step, right-looking over its 128-column leaves on `sP`, together with the `ext` columns of its
+// block row that lie above the NEXT diagonal block: each leaf's share of that solve (one product with the leaf's inverse,
+// one rank-128 update of the rows below) trails the chain by one leaf on `sX`, so that when the last leaf is done only one
+// product is left between this panel and the update of the next diagonal block.  `ev` signals sP -> sX.
+static int potrf_panel_ext(int64_t n, double* A, int64_t lda, int64_t off, double* uinv, int64_t ext, int* info,
+                           cudaStream_t sP, cudaStream_t sX, cudaEvent_t ev) {
+  double* E = A + n * lda;                       // the extension: rows [0, n), columns [n, n + ext)
+  for (int64_t j = 0; j < n; j += IB) {
+    const int64_t jb = (n - j) < IB ? (n - j) : IB, rest = n - j - jb;
+    double* Ajj = A + j + j * lda;
+    double* Arow = Ajj + jb * lda;
+    double* uj = uinv + (j / IB) * IB * IB;
+    LLA_TRY(potrf_rec(jb, Ajj, lda, off + j, uj, info, sP));
+    if (rest > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, jb, rest, Ajj, lda, uj, Arow, lda, sP, info));
+    if (sX != sP) {
+      LLA_CUDA(cudaEventRecord(ev, sP));
+      LLA_CUDA(cudaStreamWaitEvent(sX, ev, 0));
+    }
+    if (rest > 0) LLA_TRY(dgemm_dev(1, 0, rest, rest, jb, -1.0, Arow, lda, Arow, lda, 1.0, Arow + jb, lda, TRI_UPPER, sP, info));
+    LLA_TRY(dtrsm_left_inv_dev(true, 1, jb, ext, Ajj, lda, uj, E + j, lda, sX, info));
+    if (rest > 0) LLA_TRY(dgemm_dev(1, 0, rest, ext, jb, -1.0, Arow, lda, E + j, lda, 1.0, E + j + jb, lda, TRI_FULL, sX, info));
+  }
+  return 0;
+}
+
+// Blocked right-looking driver with one panel of look-ahead.  The critical chain of step k -- factor the diagonal block
+// (recursively, down to the shared-memory leaves), solve for the part of its block row above the NEXT diagonal block,
+// update that block -- runs on two high-priority streams of its own; the rest of the block row goes to a third
+// high-priority stream and the trailing updates to the main stream, which fill the machine meanwhile:
+//   sP : [diag(k-1)] potrf(k), leaf by leaf -> pot
+//   sA : [row1(k-1)] solve U(k, k+1), one leaf behind sP -> t1 | [b(k-1)] A(k+1, k+1) -= U(k, k+1)^T U(k, k+1) -> diag
+//   sR : [pot, row(k-1)] solve U(k, k+2:) | [t1] -> panel, rows final                          (beside b(k-1) of s1)
+//   s1 : ... b(k-1) | [panel] A(k+1, k+2) -= ... -> row1 | A(k+1, k+3:) -= ... -> row | b(k): rows >= k+2 -> b
 static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* info, cudaStream_t s1) {
   Context* c = ctx();
   // measured on B200 (profiles/r01_cholesky_nb.txt): n = 16384: NB 256 / 512 / 1024 / 2048 -> 101 / 78.5 / 68.6 / 68.4 ms;
@@ -97,19 +141,26 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     if (ready) LLA_TRY(ready->fn(ready->user, 0, n, s1));
     return potrf_rec(n, A, lda, 0, uinv, info, s1);
   }
-  cudaStream_t s2 = getenv("LLACUDA_NO_LOOKAHEAD") ? s1 : c->aux;
+  const bool lookahead = getenv("LLACUDA_NO_LOOKAHEAD") == nullptr;
+  cudaStream_t sP = lookahead ? c->aux : s1;
+  cudaStream_t sA = lookahead ? c->aux3 : s1;
+  cudaStream_t sR = lookahead ? c->aux2 : s1;
   cudaStream_t s0 = s1;   // the caller's stream
-  cudaEvent_t ev_row = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2], ev_diag = c->ev[3], ev_pot = c->ev[4];
+  cudaEvent_t ev_row1 = c->ev[0], ev_panel = c->ev[1], ev_start = c->ev[2], ev_diag = c->ev[3], ev_pot = c->ev[4],
+              ev_t1 = c->ev[5], ev_b = c->ev[6], ev_row = c->ev[7], ev_leaf = c->ev[8];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
-  LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
-  // Chain-bound phase (the update of a step is shorter than the panel): the panel chain moves to its own SM partition, the
-  // updates and the block-row solve to the rest, so that no kernel of the chain waits for a GEMM CTA to leave an SM.
+  LLA_CUDA(cudaStreamWaitEvent(sP, ev_start, 0));
+  if (sA != s1) LLA_CUDA(cudaStreamWaitEvent(sA, ev_start, 0));
+  if (sR != s1) LLA_CUDA(cudaStreamWaitEvent(sR, ev_start, 0));
+  // Optional (LLACUDA_CHOL_PART_N = remaining order at which to switch): the chain moves to its own SM partition, the
+  // updates and the block-row solves to the rest.  Off by default: since the chain trails its block-row solve leaf by
+  // leaf it is short enough that giving up 16-24 SMs of update throughput costs more than the isolation gains
+  // (n = 16384: 54.3 ms without, 54.8-55.1 ms with; profiles/r02_cholesky_chain.md).
   static int64_t part_n = -1;
-  if (part_n < 0) { const char* e = getenv("LLACUDA_CHOL_PART_N"); part_n = e ? atol(e) : 8192; }
-  const SmPartition* part = (part_n > 0 && s2 != s1) ? sm_partition() : nullptr;
+  if (part_n < 0) { const char* e = getenv("LLACUDA_CHOL_PART_N"); part_n = e ? atol(e) : 0; }
+  const SmPartition* part = (part_n > 0 && lookahead) ? sm_partition() : nullptr;
   bool part_on = false;
-  cudaStream_t st_trsm = s2;
-  bool rest_pending = false;  // part (a2) of the previous step: the block row right of the next diagonal block
+  bool row1_pending = false, row_pending = false, b_pending = false;
   for (int64_t k = 0; k < n; k += NB) {
     const int64_t kb = (n - k) < NB ? (n - k) : NB;
     const int64_t n2 = n - k - kb;
@@ -117,60 +168,79 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
     double* Arow = Akk + kb * lda;             // block row right of the diagonal block
     double* uk = uinv + (k / IB) * IB * IB;
     if (part && !part_on && k > 0 && (n - k) <= part_n) {
-      // the update streams of the partition follow everything queued so far; the panel stream only what panel k needs
-      // (the previous panel and the update of its diagonal block), so the switch costs no look-ahead
+      // only the update stream of the partition follows everything queued so far; the streams of the chain and of the
+      // block-row solve follow their predecessors (their inputs from the update stream arrive by the per-step events),
+      // so the switch costs no look-ahead
       LLA_CUDA(cudaEventRecord(ev_start, s1));
-      LLA_CUDA(cudaEventRecord(ev_pot, s2));
-      for (cudaStream_t t : {part->bulk, part->bulk2}) {
-        LLA_CUDA(cudaStreamWaitEvent(t, ev_start, 0));
+      LLA_CUDA(cudaEventRecord(ev_pot, sP));
+      LLA_CUDA(cudaEventRecord(ev_t1, sR));
+      LLA_CUDA(cudaEventRecord(ev_leaf, sA));
+      LLA_CUDA(cudaStreamWaitEvent(part->bulk, ev_start, 0));
+      for (cudaStream_t t : {part->bulk, part->bulk2, part->bulk3, part->panel}) {
         LLA_CUDA(cudaStreamWaitEvent(t, ev_pot, 0));
+        LLA_CUDA(cudaStreamWaitEvent(t, ev_t1, 0));
+        LLA_CUDA(cudaStreamWaitEvent(t, ev_leaf, 0));
       }
-      LLA_CUDA(cudaStreamWaitEvent(part->panel, ev_pot, 0));
-      LLA_CUDA(cudaStreamWaitEvent(part->panel, ev_diag, 0));
-      s1 = part->bulk; s2 = part->panel; st_trsm = part->bulk2;
+      s1 = part->bulk; sP = part->panel; sA = part->bulk2; sR = part->bulk3;
       part_on = true;
       trace_mark(s1, "chol.partition", k, part->sm_panel);
     }
-    // ---- panel k on s2: the diagonal block needs only part (a1) of the previous update, the block row also (a2)
-    trace_mark(s2, "chol.panel>", k, kb);
-    if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
-    LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, s2));
-    trace_mark(s2, "chol.trsm>", k, n2);
-    if (part_on) {   // the block-row solve is a wide GEMM-shaped job: on the large partition
-      LLA_CUDA(cudaEventRecord(ev_pot, s2));
-      LLA_CUDA(cudaStreamWaitEvent(st_trsm, ev_pot, 0));
+    // ---- the chain: diagonal block k and, trailing it leaf by leaf on sA, the block row above the next diagonal block
+    trace_mark(sP, "chol.panel>", k, kb);
+    if (ready && k == 0) {
+      LLA_TRY(ready->fn(ready->user, 0, kb, sP));
+      if (sA != sP) LLA_TRY(ready->fn(ready->user, 0, kb, sA));
     }
-    if (rest_pending) LLA_CUDA(cudaStreamWaitEvent(st_trsm, ev_row, 0));
-    if (n2 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n2, Akk, lda, uk, Arow, lda, st_trsm, info));
-    trace_mark(st_trsm, "chol.panel<", k, kb);
-    LLA_CUDA(cudaEventRecord(ev_panel, st_trsm));
-    if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, st_trsm, nullptr));  // block row k of U is final
-    if (n2 <= 0) break;
-    // ---- trailing update of step k on s1
-    LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
+    if (n2 <= 0) {
+      LLA_TRY(potrf_rec(kb, Akk, lda, k, uk, info, sP));
+      LLA_CUDA(cudaEventRecord(ev_panel, sP));
+      if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, sP, nullptr));
+      break;
+    }
     const int64_t kb_next = n2 < NB ? n2 : NB;
-    double* Anext = Arow + kb;                   // A[k+kb, k+kb]
-    // (a1) the next diagonal block, (a2) the rest of the next panel's block row: rows [k+kb, k+kb+kb_next), columns [k+kb, n)
-    trace_mark(s1, "chol.updA>", k, n2);
-    if (ready && k == 0) LLA_TRY(ready->fn(ready->user, kb, kb + kb_next, s1));
-    LLA_TRY(dgemm_dev(1, 0, kb_next, kb_next, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, s1, info));
-    LLA_CUDA(cudaEventRecord(ev_diag, s1));
-    LLA_CUDA(cudaStreamWaitEvent(s2, ev_diag, 0));
-    rest_pending = n2 > kb_next;
-    if (rest_pending) {
-      LLA_TRY(dgemm_dev(1, 0, kb_next, n2 - kb_next, kb, -1.0, Arow, lda, Arow + kb_next * lda, lda, 1.0,
-                        Anext + kb_next * lda, lda, TRI_FULL, s1, info));
-      LLA_CUDA(cudaEventRecord(ev_row, s1));
-    }
-    trace_mark(s1, "chol.updA<", k, n2);
-    // (b) the rest: rows [k+kb+kb_next, n)
-    const int64_t n3 = n2 - kb_next;
+    const int64_t n3 = n2 - kb_next;           // columns right of the next diagonal block
+    double* Anext = Arow + kb;                 // A[k+kb, k+kb]
+    if (row1_pending) LLA_CUDA(cudaStreamWaitEvent(sA, ev_row1, 0));
+    LLA_TRY(potrf_panel_ext(kb, Akk, lda, k, uk, kb_next, info, sP, sA, ev_leaf));
+    LLA_CUDA(cudaEventRecord(ev_pot, sP));
+    LLA_CUDA(cudaEventRecord(ev_t1, sA));
+    // the next diagonal block
+    if (b_pending) LLA_CUDA(cudaStreamWaitEvent(sA, ev_b, 0));
+    if (ready && k == 0) LLA_TRY(ready->fn(ready->user, kb, kb + kb_next, sA));
+    trace_mark(sA, "chol.diag>", k, kb_next);
+    LLA_TRY(dgemm_dev(1, 0, kb_next, kb_next, kb, -1.0, Arow, lda, Arow, lda, 1.0, Anext, lda, TRI_UPPER, sA, info));
+    LLA_CUDA(cudaEventRecord(ev_diag, sA));
+    if (sA != sP) LLA_CUDA(cudaStreamWaitEvent(sP, ev_diag, 0));
+    trace_mark(sA, "chol.diag<", k, kb_next);
+    // ---- the rest of the block row on sR, beside whatever s1 is still doing for step k - 1
+    LLA_CUDA(cudaStreamWaitEvent(sR, ev_pot, 0));
+    if (row_pending) LLA_CUDA(cudaStreamWaitEvent(sR, ev_row, 0));
+    trace_mark(sR, "chol.trsm2>", k, n3);
+    if (n3 > 0) LLA_TRY(dtrsm_left_inv_dev(true, 1, kb, n3, Akk, lda, uk, Arow + kb_next * lda, lda, sR, info));
+    LLA_CUDA(cudaStreamWaitEvent(sR, ev_t1, 0));
+    LLA_CUDA(cudaEventRecord(ev_panel, sR));
+    trace_mark(sR, "chol.panel<", k, kb);
+    if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, sR, nullptr));  // block row k of U is final
+    // ---- the trailing update of step k on s1, from top to bottom
+    LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
+    row1_pending = row_pending = b_pending = false;
     if (n3 > 0) {
-      // k-split of the big update: shorter-lived CTAs, so that the kernels of the panel chain (high-priority
-      // stream) find a free SM sooner (a 128x128 tile with k = 1024 occupies its SM for ~150 us)
-      static int64_t ks_env = -1;
-      if (ks_env < 0) { const char* e = getenv("LLACUDA_CHOL_KSPLIT"); ks_env = e ? atoi(e) : 0; }
-      const int64_t ks = ks_env > 0 ? ks_env : kb;
+      // block row k+1: first the columns above diagonal block k+2 (the chain needs them next), then the rest
+      trace_mark(s1, "chol.updA>", k, n3);
+      if (ready && k == 0) LLA_TRY(ready->fn(ready->user, kb, kb + kb_next, s1));
+      const int64_t w1 = n3 < NB ? n3 : NB;
+      LLA_TRY(dgemm_dev(1, 0, kb_next, w1, kb, -1.0, Arow, lda, Arow + kb_next * lda, lda, 1.0, Anext + kb_next * lda, lda,
+                        TRI_FULL, s1, info));
+      LLA_CUDA(cudaEventRecord(ev_row1, s1));
+      row1_pending = true;
+      if (n3 > w1) {
+        LLA_TRY(dgemm_dev(1, 0, kb_next, n3 - w1, kb, -1.0, Arow, lda, Arow + (kb_next + w1) * lda, lda, 1.0,
+                          Anext + (kb_next + w1) * lda, lda, TRI_FULL, s1, info));
+        LLA_CUDA(cudaEventRecord(ev_row, s1));
+        row_pending = true;
+      }
+      trace_mark(s1, "chol.updA<", k, n3);
+      // rows [k+kb+kb_next, n)
       if (ready && k == 0) {
         // first step: the update is separable by block row, so each block row starts as soon as it is on the device
         const int64_t t0 = kb + kb_next;                     // first row / column of this part of the trailing matrix
@@ -180,15 +250,14 @@ static int potrf_blocked(int64_t n, double* A, int64_t lda, double* uinv, int* i
           const double* P = Arow + (r0 - kb) * lda;          // U(k, r0:)
           LLA_TRY(dgemm_dev(1, 0, r1 - r0, n - r0, kb, -1.0, P, lda, P, lda, 1.0, A + r0 + r0 * lda, lda, TRI_UPPER, s1, info));
         }
-      } else
-      for (int64_t kk = 0; kk < kb; kk += ks) {
-        const int64_t kw = (kb - kk) < ks ? (kb - kk) : ks;
-        const double* P = Arow + kk + kb_next * lda;
-        LLA_TRY(dgemm_dev(1, 0, n3, n3, kw, -1.0, P, lda, P, lda, 1.0, Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info,
-                          getenv("LLACUDA_CHOL_RESERVE") ? GEMM_RESERVE_SMS : GEMM_AUTO));
+      } else {
+        const double* P = Arow + kb_next * lda;
+        LLA_TRY(dgemm_dev(1, 0, n3, n3, kb, -1.0, P, lda, P, lda, 1.0, Anext + kb_next + kb_next * lda, lda, TRI_UPPER, s1, info));
       }
+      LLA_CUDA(cudaEventRecord(ev_b, s1));
+      b_pending = true;
+      trace_mark(s1, "chol.updB<", k, n3);
     }
-    trace_mark(s1, "chol.updB<", k, n3);
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   if (part_on) {   // back to the caller's stream
