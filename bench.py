@@ -730,9 +730,12 @@ def main():
             "workload": "configs[3]: 200 000 independent 32 x 32 double systems (dgesv, 1 rhs), one slice per GPU, no collective",
             "ms": b["ms"], "systems_per_s": 200_000 / (b["ms"] * 1e-3), "max_scaled_residual": b["max_scaled_residual"],
             "info_nonzero": b["info_nonzero"],
-            "roofline": {"kernel": "lla_dgesv_batched_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm * world, "unit": "GB/s",
+            "roofline": {"kernel": "lla_dgesv_batched_smem_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm * world, "unit": "GB/s",
                          "frac": gbs / (hbm * world), "algorithmic_bytes_per_system": 8704,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured) x GPUs; L2 flushed between launches"}}
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured) x GPUs; L2 flushed between launches",
+                         "note": "DRAM traffic is the algorithmic minimum (ncu: 1.74 GB per launch) but the kernel is issue-bound, not "
+                                 "HBM-bound: DGETF2's separately rounded multiply and subtract cost 1 800 FP64-pipe instructions per "
+                                 "system at 2 issue cycles each = 0.62 ms per 200 000 systems on 148 SMs (profiles/r02_batched.md)"}}
         if rank == 0:
             sg = sgemm_leg(local_rank)
             bf16 = 1663.5

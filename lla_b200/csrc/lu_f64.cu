@@ -599,6 +599,33 @@ static int lu_rec(const LuCtx& L, int64_t j0, int64_t m, int64_t n) {
   return 0;
 }
 
+// Experiment (LLACUDA_LU_PANEL_RL=1): the panel of a blocked step right-looking over its 32-column leaves -- leaf (+ its
+// interchanges on the other panel columns), 32-row solve of the columns to its right, rank-32 update below: 66 launches
+// per 512-column panel instead of the recursion's 76, but 15 passes over the panel with k = 32 GEMMs.  Measured slower
+// (n = 16384: 150.3 against 146.1 ms, profiles/r02_lu_chain.md); the recursion stays the default.
+static int lu_panel_rl(const LuCtx& L, int64_t k, int64_t m, int64_t kb) {
+  for (int64_t c = 0; c < kb; c += PW) {
+    const int64_t w = (kb - c) < PW ? (kb - c) : PW;
+    const int64_t j0 = k + c, R = kb - c - w, mr = m - c;
+    if (mr <= 0) break;
+    LLA_TRY(lu_leaf(L, j0, mr, (int)w));
+    double* A11 = L.A + j0 + j0 * L.lda;
+    double* A12 = A11 + w * L.lda;
+    if (R > 0) {
+      LLA_TRY(dtrsm_left_dev(false, 0, true, w < mr ? w : mr, R, A11, L.lda, A12, L.lda, L.st));
+      if (mr > w) LLA_TRY(dgemm_dev(0, 0, mr - w, R, w, -1.0, A11 + w, L.lda, A12, L.lda, 1.0, A12 + w, L.lda, TRI_FULL, L.st));
+    }
+    const int64_t e = c + w;   // columns of the panel finished so far
+    if (e % IB == 0 || e == kb) {   // a 128-column block of L is final: invert its unit-lower diagonal block
+      const int64_t bs = ((e - 1) / IB) * IB;
+      int64_t r = e - bs;
+      if (m - bs < r) r = m - bs;
+      if (r > 0) LLA_TRY(dtrtri_blocks_dev(false, true, r, L.A + (k + bs) + (k + bs) * L.lda, L.lda, L.linv + ((k + bs) / IB) * IB * IB, L.st));
+    }
+  }
+  return 0;
+}
+
 // columns [c0, c1) right of panel (k, kb): interchanges, U12 = L11^-1 A12, A22 -= A21 U12
 static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st, int hint = GEMM_AUTO) {
   if (c1 <= c0) return 0;
@@ -668,7 +695,9 @@ static int lu_blocked(LuCtx L) {
     P.st = s2; P.swap_c0 = k; P.swap_c1 = k + kb;
     if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
     trace_mark(s2, "lu.panel>", k, kb);
-    LLA_TRY(lu_rec(P, k, L.M - k, kb));
+    static const bool panel_rl = getenv("LLACUDA_LU_PANEL_RL") != nullptr;
+    if (panel_rl) LLA_TRY(lu_panel_rl(P, k, L.M - k, kb));
+    else LLA_TRY(lu_rec(P, k, L.M - k, kb));
     trace_mark(s2, "lu.panel<", k, kb);
     LLA_CUDA(cudaEventRecord(ev_panel, s2));
     // ---- interchanges of the finished columns [0, k) on s3 (after the update that still reads them)

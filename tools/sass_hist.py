@@ -9,7 +9,7 @@ import sys
 so = "lla_b200/libllacuda.so"
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 want = ["lla_dgemm_kernel", "lla_zgemm_kernel", "lla_sgemm_tcgen05_kernel", "lla_dgetf2_panel_kernel", "lla_dpotrf128_kernel",
-        "lla_dgesv_batched_kernel", "lla_xgemm_simt_kernel", "lla_xgetf2_panel_kernel", "lla_convert_kernel", "lla_copy_blocks_kernel",
+        "lla_dgesv_batched_smem_kernel", "lla_xgemm_simt_kernel", "lla_xgetf2_panel_kernel", "lla_convert_kernel", "lla_copy_blocks_kernel",
         "lla_dlaswp_dense_kernel", "lla_swap_pack_kernel"]
 interesting = ["DMMA", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "HMMA", "REDUX", "DFMA", "DMUL", "DADD",
                "FFMA", "SHFL", "LDS", "STS", "LDG", "STG", "BAR", "SYNCS", "MUFU"]
