@@ -492,6 +492,17 @@ struct LuCtx {
   int64_t swap_c0, swap_c1;  // columns that receive a leaf's interchanges right after the leaf
   cudaStream_t st;
   int per_sm = 1;            // co-resident panel CTAs per SM (occupancy of the leaf kernel)
+  struct LuExt* ext = nullptr;   // chain-bound phase: the next panel's columns trail this panel block by block
+};
+
+// The columns [c0, c1) of the NEXT panel, updated on stream `sx` one 128-column block behind the panel chain (see
+// lu_blocked).  The update of block b reads the L columns of block b below the diagonal; the panel's next interchange of
+// those columns (the first leaf of block b + 1) therefore waits for `ev_y`.
+struct LuExt {
+  int64_t c0 = 0, c1 = 0;
+  cudaStream_t sx = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_y = nullptr;
+  bool pending = false;      // a block update is in flight on sx: the next interchange of the panel's columns waits for it
 };
 
 static std::atomic<unsigned> g_panel_epoch{1};
@@ -554,6 +565,10 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   else if (pr == 256) LLA_TRY(launch_panel<256>(L, P, m, w, j0, epoch, dbg));
   else LLA_TRY(launch_panel<512>(L, P, m, w, j0, epoch, dbg));
   if (leaf_trace) trace_mark(L.st, "lu.leafK<", j0, m);
+  if (L.ext && L.ext->pending) {   // the trailing block update still reads the columns left of this leaf
+    LLA_CUDA(cudaStreamWaitEvent(L.st, L.ext->ev_y, 0));
+    L.ext->pending = false;
+  }
   // interchange the other columns of the swap window now: [swap_c0, j0) and [j0+w, swap_c1)
   int64_t npiv = m < w ? m : w;
   LLA_TRY(dlaswp_skip_dev(L.swap_c1 - L.swap_c0, j0 - L.swap_c0, j0 + w - L.swap_c0, L.A + L.swap_c0 * L.lda, L.lda,
@@ -595,6 +610,21 @@ static int lu_rec(const LuCtx& L, int64_t j0, int64_t m, int64_t n) {
   if (j0 % IB == 0 && n <= IB && (n == IB || j0 + n == L.N || m <= n)) {
     int64_t r = mn;  // rows/cols of the diagonal block that exist
     LLA_TRY(dtrtri_blocks_dev(false, true, r, A11, L.lda, L.linv + (j0 / IB) * IB * IB, L.st));
+    if (L.ext && n == IB && m >= IB) {
+      // this block's share of the next panel's columns: interchanges, U = L_bb^-1 A, rows below -= L_b U
+      LuExt& X = *L.ext;
+      const int64_t nc = X.c1 - X.c0;
+      double* E = L.A + j0 + X.c0 * L.lda;
+      LLA_CUDA(cudaEventRecord(X.ev_x, L.st));
+      LLA_CUDA(cudaStreamWaitEvent(X.sx, X.ev_x, 0));
+      LLA_TRY(dlaswp_dev(nc, L.A + X.c0 * L.lda, L.lda, j0, j0 + IB, L.ipiv, true, X.sx));
+      LLA_TRY(dtrsm_left_inv_dev(false, 0, IB, nc, A11, L.lda, L.linv + (j0 / IB) * IB * IB, E, L.lda, X.sx));
+      if (m > IB) {
+        LLA_TRY(dgemm_dev(0, 0, m - IB, nc, IB, -1.0, A11 + IB, L.lda, E, L.lda, 1.0, E + IB, L.lda, TRI_FULL, X.sx));
+        LLA_CUDA(cudaEventRecord(X.ev_y, X.sx));
+        X.pending = true;
+      }
+    }
   }
   return 0;
 }
@@ -672,6 +702,19 @@ static int lu_blocked(LuCtx L) {
   const SmPartition* part = part_m > 0 ? sm_partition() : nullptr;
   bool part_on = false;
   bool have_b = false;
+  // Chain-bound phase, second measure: the update of the NEXT panel's columns (interchanges, solve, product -- "updA", 0.6 ms
+  // per step after a panel of 1.8-2.1 ms) trails the panel block by block on a stream of its own, so that only the last
+  // 128-column block's share is left between two panels (0.3 ms).  Only in the chain-bound phase (remaining rows <=
+  // LLACUDA_LU_EXT_M): the trailing stream needs the previous step's update of those columns, which that update therefore
+  // does first and signals separately (ev_b1); earlier in the factorisation the panel would stall behind it.  Trailing
+  // leaf by leaf (32 columns) was measured slower: 48 small launches per panel lag the chain's interchanges
+  // (profiles/r02_lu_chain.md).
+  static int64_t ext_m = -1;
+  if (ext_m < 0) { const char* e = getenv("LLACUDA_LU_EXT_M"); ext_m = e ? atol(e) : 9216; }
+  LuExt X;
+  X.ev_x = c->ev[8]; X.ev_y = c->ev[9];
+  cudaEvent_t ev_b1 = c->ev[10];
+  bool have_b1 = false;
   for (int64_t k = 0; k < mn; k += NB) {
     const int64_t kb = (mn - k) < NB ? (mn - k) : NB;
     if (part && !part_on && k > 0 && (L.M - k) <= part_m &&
@@ -693,6 +736,18 @@ static int lu_blocked(LuCtx L) {
     // ---- panel k on s2
     LuCtx P = L;
     P.st = s2; P.swap_c0 = k; P.swap_c1 = k + kb;
+    const int64_t ext_kb = (k + kb < mn) ? ((mn - k - kb) < NB ? (mn - k - kb) : NB) : 0;
+    const bool b1_now = have_b1;   // the previous step updated this step's extension columns first and recorded ev_b1
+    have_b1 = false;
+    const bool use_ext = k > 0 && ext_kb > 0 && kb % IB == 0 && (L.M - k) <= ext_m && L.M - k - kb >= IB && s2 != s1;
+    if (use_ext) {
+      X.c0 = k + kb; X.c1 = k + kb + ext_kb; X.pending = false;
+      X.sx = part_on ? part->bulk3 : c->aux3;
+      // the columns received the previous step's update on s1 (ev_b) and, before that switch, nothing else is queued on sx
+      if (b1_now) LLA_CUDA(cudaStreamWaitEvent(X.sx, ev_b1, 0));
+      else if (have_b) LLA_CUDA(cudaStreamWaitEvent(X.sx, ev_b, 0));
+      P.ext = &X;
+    }
     if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
     trace_mark(s2, "lu.panel>", k, kb);
     static const bool panel_rl = getenv("LLACUDA_LU_PANEL_RL") != nullptr;
@@ -713,12 +768,20 @@ static int lu_blocked(LuCtx L) {
     LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
     const int64_t next_kb = (k + kb < mn) ? ((mn - c0) < NB ? (mn - c0) : NB) : 0;
     const int64_t c1 = c0 + next_kb;
-    trace_mark(s1, "lu.updA>", k, c1 - c0);
-    if (ready && k == 0 && c1 > c0) LLA_TRY(ready->fn(ready->user, c0, c1, s1));
-    LLA_TRY(lu_update_cols(L, k, kb, c0, c1, s1));
-    trace_mark(s1, "lu.updA<", k, c1 - c0);
-    LLA_CUDA(cudaEventRecord(ev_a, s1));
-    LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
+    if (use_ext) {
+      // the next panel's columns are done on sx (the last block's share was queued when the panel returned)
+      trace_mark(X.sx, "lu.ext<", k, c1 - c0);
+      LLA_CUDA(cudaEventRecord(ev_a, X.sx));
+      LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
+      LLA_CUDA(cudaStreamWaitEvent(s1, ev_a, 0));   // rows-final hook and the end of the call see the whole block row
+    } else {
+      trace_mark(s1, "lu.updA>", k, c1 - c0);
+      if (ready && k == 0 && c1 > c0) LLA_TRY(ready->fn(ready->user, c0, c1, s1));
+      LLA_TRY(lu_update_cols(L, k, kb, c0, c1, s1));
+      trace_mark(s1, "lu.updA<", k, c1 - c0);
+      LLA_CUDA(cudaEventRecord(ev_a, s1));
+      LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
+    }
     // the rest of the update runs as a persistent GEMM that leaves `reserve` SMs to the panel stream:
     // the factorisation is bound by the panel chain, so the chain gets SMs of its own
     static int reserve = -1;
@@ -731,8 +794,19 @@ static int lu_blocked(LuCtx L) {
         LLA_TRY(ready->fn(ready->user, cc, ce, s1));
         LLA_TRY(lu_update_cols(L, k, kb, cc, ce, s1));
       }
-    } else
-    LLA_TRY(lu_update_cols(L, k, kb, c1, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
+    } else {
+      // when the next step trails its extension, that extension's columns (the first NB of this update) come first and
+      // signal on their own, so the trailing stream can start while the rest of this update is still running
+      int64_t cs = c1;
+      const bool next_ext = ext_m > 0 && s2 != s1 && (L.M - c0) <= ext_m && c1 < L.N;
+      if (next_ext) {
+        cs = c1 + NB < L.N ? c1 + NB : L.N;
+        LLA_TRY(lu_update_cols(L, k, kb, c1, cs, s1));
+        LLA_CUDA(cudaEventRecord(ev_b1, s1));
+        have_b1 = true;
+      }
+      LLA_TRY(lu_update_cols(L, k, kb, cs, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
+    }
     trace_mark(s1, "lu.updB<", k, L.N - c1);
     LLA_CUDA(cudaEventRecord(ev_b, s1));
     have_b = true;
