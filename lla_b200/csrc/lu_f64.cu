@@ -715,6 +715,7 @@ static int lu_blocked(LuCtx L) {
   X.ev_x = c->ev[8]; X.ev_y = c->ev[9];
   cudaEvent_t ev_b1 = c->ev[10];
   bool have_b1 = false;
+  static const bool side_a = getenv("LLACUDA_LU_NO_SIDE_A") == nullptr;
   for (int64_t k = 0; k < mn; k += NB) {
     const int64_t kb = (mn - k) < NB ? (mn - k) : NB;
     if (part && !part_on && k > 0 && (L.M - k) <= part_m &&
@@ -768,12 +769,28 @@ static int lu_blocked(LuCtx L) {
     LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
     const int64_t next_kb = (k + kb < mn) ? ((mn - c0) < NB ? (mn - c0) : NB) : 0;
     const int64_t c1 = c0 + next_kb;
+    bool join_a = false;   // s1 has to see ev_a (recorded on another stream) before the block row counts as final
     if (use_ext) {
       // the next panel's columns are done on sx (the last block's share was queued when the panel returned)
       trace_mark(X.sx, "lu.ext<", k, c1 - c0);
       LLA_CUDA(cudaEventRecord(ev_a, X.sx));
       LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
-      LLA_CUDA(cudaStreamWaitEvent(s1, ev_a, 0));   // rows-final hook and the end of the call see the whole block row
+      join_a = true;
+    } else if (side_a && c1 > c0) {
+      // the next panel's columns on the side stream, as soon as the previous update has done them (its first piece,
+      // ev_b1): the next panel starts while the rest of that update is still running, and s1 goes from update to update
+      cudaStream_t sx = part_on ? part->bulk3 : c->aux3;
+      LLA_CUDA(cudaStreamWaitEvent(sx, ev_panel, 0));
+      if (b1_now) LLA_CUDA(cudaStreamWaitEvent(sx, ev_b1, 0));
+      else if (have_b) LLA_CUDA(cudaStreamWaitEvent(sx, ev_b, 0));
+      else LLA_CUDA(cudaStreamWaitEvent(sx, ev_start, 0));
+      trace_mark(sx, "lu.updA>", k, c1 - c0);
+      if (ready && k == 0) LLA_TRY(ready->fn(ready->user, c0, c1, sx));
+      LLA_TRY(lu_update_cols(L, k, kb, c0, c1, sx));
+      trace_mark(sx, "lu.updA<", k, c1 - c0);
+      LLA_CUDA(cudaEventRecord(ev_a, sx));
+      LLA_CUDA(cudaStreamWaitEvent(s2, ev_a, 0));
+      join_a = true;
     } else {
       trace_mark(s1, "lu.updA>", k, c1 - c0);
       if (ready && k == 0 && c1 > c0) LLA_TRY(ready->fn(ready->user, c0, c1, s1));
@@ -798,7 +815,7 @@ static int lu_blocked(LuCtx L) {
       // when the next step trails its extension, that extension's columns (the first NB of this update) come first and
       // signal on their own, so the trailing stream can start while the rest of this update is still running
       int64_t cs = c1;
-      const bool next_ext = ext_m > 0 && s2 != s1 && (L.M - c0) <= ext_m && c1 < L.N;
+      const bool next_ext = s2 != s1 && c1 < L.N && (side_a || (ext_m > 0 && (L.M - c0) <= ext_m));
       if (next_ext) {
         cs = c1 + NB < L.N ? c1 + NB : L.N;
         LLA_TRY(lu_update_cols(L, k, kb, c1, cs, s1));
@@ -810,6 +827,7 @@ static int lu_blocked(LuCtx L) {
     trace_mark(s1, "lu.updB<", k, L.N - c1);
     LLA_CUDA(cudaEventRecord(ev_b, s1));
     have_b = true;
+    if (join_a) LLA_CUDA(cudaStreamWaitEvent(s1, ev_a, 0));
     // rows [k, k+kb) are final: U12 was solved at the head of this update, the L part received its last
     // interchanges from this panel (later panels only touch rows below)
     if (const RowsFinalHook* h = rows_final_hook()) LLA_TRY(h->fn(h->user, k, k + kb, s1, k > 0 ? s3 : nullptr));
