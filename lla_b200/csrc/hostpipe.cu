@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -17,9 +18,47 @@ namespace llacuda {
 
 namespace {
 
-constexpr size_t SLAB_BYTES = size_t(16) << 20;
-constexpr int NSLAB = 3;                       // per direction and device
-constexpr size_t PIECE_BYTES = size_t(1) << 20;
+// LLACUDA_PIPE_STATS=1: where the staging threads spend their time (printed at exit): host copies, waits for a slab's
+// DMA, bytes -- per direction
+struct PipeStats {
+  std::atomic<long long> bytes{0}, copy_us{0}, wait_us{0}, busy_us{0}, xfers{0};
+};
+PipeStats g_stats[2];
+bool stats_on() { static const bool on = getenv("LLACUDA_PIPE_STATS") != nullptr; return on; }
+long long now_us() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long long)ts.tv_sec * 1000000ll + ts.tv_nsec / 1000;
+}
+struct StatsDump {
+  ~StatsDump() {
+    if (!stats_on()) return;
+    for (int d = 0; d < 2; d++) {
+      const PipeStats& t = g_stats[d];
+      if (!t.xfers.load()) continue;
+      fprintf(stderr, "llacuda pipe %s: %lld transfers, %.1f MB, busy %.1f ms (host copies %.1f ms = %.1f GB/s, slab / DMA waits %.1f ms)\n",
+              d == 0 ? "up  " : "down", t.xfers.load(), t.bytes.load() / 1e6, t.busy_us.load() / 1e3, t.copy_us.load() / 1e3,
+              t.copy_us.load() ? t.bytes.load() / 1e3 / t.copy_us.load() : 0.0, t.wait_us.load() / 1e3);
+    }
+  }
+} g_stats_dump;
+
+// Slab geometry (per direction and device).  Every staged byte crosses the host's memory three times (source -> slab by
+// the copy threads, slab -> device by the DMA engine), so the ring is kept small enough to stay in the last-level cache
+// between the copy and the DMA that follows it, and fine-grained enough that copy and DMA of one transfer overlap;
+// LLACUDA_SLAB_MB / LLACUDA_NSLAB / LLACUDA_PIECE_KB override.  Measured (profiles/r02_pageable_probe.log, n = 16384,
+// dgesv_ / dpotrf_ from pageable memory): 3 x 16 MiB slabs 256 / 132 ms, 8 x 4 MiB slabs with 256 KiB pieces 204 / 89 ms.
+constexpr int NSLAB_MAX = 8;
+size_t env_size(const char* name, size_t dflt, size_t lo, size_t hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  long v = atol(e);
+  if (v < (long)lo) v = (long)lo;
+  if (v > (long)hi) v = (long)hi;
+  return (size_t)v;
+}
+const size_t SLAB_BYTES = env_size("LLACUDA_SLAB_MB", 4, 1, 64) << 20;
+const int NSLAB = (int)env_size("LLACUDA_NSLAB", 8, 2, NSLAB_MAX);
+const size_t PIECE_BYTES = env_size("LLACUDA_PIECE_KB", 256, 64, 4096) << 10;
 
 // ------------------------------------------------------------------ parallel host memcpy
 struct Batch {
@@ -34,22 +73,21 @@ class CopyPool {
  public:
   static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }
   // copies every piece, using the helpers and the calling thread; returns when all are done
-  void run(std::vector<Piece>& pieces) {
+  // `first`: uploads -- they gate the computation, downloads only its end -- are served before queued download pieces
+  void run(std::vector<Piece>& pieces, bool first) {
     if (pieces.empty()) return;
     Batch b;
     b.remaining = (int)pieces.size();
     {
       std::lock_guard<std::mutex> lk(mu_);
-      for (auto& p : pieces) { p.batch = &b; q_.push_back(p); }
+      for (auto& p : pieces) { p.batch = &b; (first ? q_first_ : q_).push_back(p); }
     }
     cv_.notify_all();
-    for (;;) {  // help until this batch's pieces are all taken, then wait for the stragglers
+    for (;;) {  // help until the queues are empty, then wait for this batch's stragglers
       Piece p;
       {
         std::lock_guard<std::mutex> lk(mu_);
-        if (q_.empty()) break;
-        p = q_.front();
-        q_.pop_front();
+        if (!take(p)) break;
       }
       work(p);
     }
@@ -80,16 +118,22 @@ class CopyPool {
       Piece p;
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return !q_.empty(); });
-        p = q_.front();
-        q_.pop_front();
+        cv_.wait(lk, [&] { return !q_.empty() || !q_first_.empty(); });
+        take(p);
       }
       work(p);
     }
   }
+  bool take(Piece& p) {   // under mu_
+    std::deque<Piece>& q = !q_first_.empty() ? q_first_ : q_;
+    if (q.empty()) return false;
+    p = q.front();
+    q.pop_front();
+    return true;
+  }
   std::mutex mu_;
   std::condition_variable cv_;
-  std::deque<Piece> q_;
+  std::deque<Piece> q_, q_first_;
 };
 
 }  // namespace
@@ -167,9 +211,9 @@ class Pipe {
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<std::shared_ptr<XferState>> q_;
-  char* slab_[NSLAB] = {};
-  cudaEvent_t slab_ev_[MAX_DEV][NSLAB] = {};
-  cudaEvent_t last_[NSLAB] = {};      // event of the DMA that used the slab last
+  char* slab_[NSLAB_MAX] = {};
+  cudaEvent_t slab_ev_[MAX_DEV][NSLAB_MAX] = {};
+  cudaEvent_t last_[NSLAB_MAX] = {};      // event of the DMA that used the slab last
   cudaStream_t stream_[MAX_DEV] = {};
 
   static void fail(XferState& x, cudaError_t e, int line) {
@@ -184,11 +228,11 @@ class Pipe {
 
   void prepare(XferState& x) {
     PIPE_CUDA(cudaSetDevice(x.dev));
-    for (auto& s : slab_)
-      if (!s) PIPE_CUDA(cudaHostAlloc((void**)&s, SLAB_BYTES, cudaHostAllocPortable));
+    for (int i = 0; i < NSLAB; i++)
+      if (!slab_[i]) PIPE_CUDA(cudaHostAlloc((void**)&slab_[i], SLAB_BYTES, cudaHostAllocPortable));
     if (!stream_[x.dev]) {
       PIPE_CUDA(cudaStreamCreateWithFlags(&stream_[x.dev], cudaStreamNonBlocking));
-      for (auto& e : slab_ev_[x.dev]) PIPE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (int i = 0; i < NSLAB; i++) PIPE_CUDA(cudaEventCreateWithFlags(&slab_ev_[x.dev][i], cudaEventDisableTiming));
     }
   }
 
@@ -201,9 +245,12 @@ class Pipe {
     for (size_t i = 0; i < chunks.size(); i++) {
       const Chunk& ch = chunks[i];
       const int slot = (int)(i % NSLAB);
+      const long long t0 = stats_on() ? now_us() : 0;
       if (last_[slot]) PIPE_CUDA(cudaEventSynchronize(last_[slot]));   // the DMA that read this slab has finished
+      const long long t1 = stats_on() ? now_us() : 0;
       chunk_pieces(pieces, ch, x.host, x.hpitch, slab_[slot], true);
-      CopyPool::get().run(pieces);
+      CopyPool::get().run(pieces, true);
+      if (stats_on()) { g_stats[0].wait_us += t1 - t0; g_stats[0].copy_us += now_us() - t1; g_stats[0].bytes += (long long)(ch.w * ch.cols); }
       PIPE_CUDA(cudaMemcpy2DAsync(x.devp + ch.c0 * x.dpitch + ch.off, x.dpitch, slab_[slot], ch.w, ch.w, ch.cols,
                                   cudaMemcpyHostToDevice, st));
       PIPE_CUDA(cudaEventRecord(slab_ev_[x.dev][slot], st));
@@ -222,10 +269,13 @@ class Pipe {
     const size_t nc = chunks.size();
     auto drain = [&](size_t i) -> bool {
       const int slot = (int)(i % NSLAB);
+      const long long t0 = stats_on() ? now_us() : 0;
       cudaError_t e = cudaEventSynchronize(slab_ev_[x.dev][slot]);
       if (e != cudaSuccess) { fail(x, e, __LINE__); return false; }
+      const long long t1 = stats_on() ? now_us() : 0;
       chunk_pieces(pieces, chunks[i], x.host, x.hpitch, slab_[slot], false);
-      CopyPool::get().run(pieces);
+      CopyPool::get().run(pieces, false);
+      if (stats_on()) { g_stats[1].wait_us += t1 - t0; g_stats[1].copy_us += now_us() - t1; g_stats[1].bytes += (long long)(chunks[i].w * chunks[i].cols); }
       return true;
     };
     for (size_t i = 0; i < nc; i++) {
@@ -250,7 +300,9 @@ class Pipe {
         s = q_.front();
         q_.pop_front();
       }
+      const long long tb = stats_on() ? now_us() : 0;
       if (up_) upload(*s); else download(*s);
+      if (stats_on()) { g_stats[up_ ? 0 : 1].busy_us += now_us() - tb; g_stats[up_ ? 0 : 1].xfers += 1; }
       {
         std::lock_guard<std::mutex> lk(s->mu);
         s->enq = true;
