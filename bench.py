@@ -56,7 +56,7 @@ def flops(n, nrhs=NRHS):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region (a step at N = 8 is 160 ms)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)],
+                                          "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -623,6 +623,7 @@ def e2e_leg(args, world, pageable, steps):
     for fn in (gemm, gesv, potrf):
         fn.restype = None
     te = {"mm": 0.0, "solve": 0.0, "cholesky": 0.0}
+    per_step_ms = []
     resid = None
     for it in range(1 + steps):
         timed = it >= 1
@@ -644,12 +645,14 @@ def e2e_leg(args, world, pageable, steps):
         assert hinfo.value == 0, (names[2], hinfo.value, _lib.last_error())
         if timed:
             te["mm"] += t1 - t0; te["solve"] += t3 - t2; te["cholesky"] += t5 - t4
+            per_step_ms.append([round((t1 - t0) * 1e3, 1), round((t3 - t2) * 1e3, 1), round((t5 - t4) * 1e3, 1)])
     f = flops(n, nrhs)
     total = sum(te.values())
     for p in hbuf:
         lib.llacuda_host_free(p)
     return {"value": sum(f.values()) * steps / total / 1e9, "ops": {k: f[k] * steps / te[k] / 1e9 for k in te},
-            "steps": steps, "solve_scaled_residual": resid, "entry_points": list(names)}
+            "steps": steps, "per_step_ms_mm_solve_cholesky": per_step_ms, "solve_scaled_residual": resid,
+            "entry_points": list(names)}
 
 
 def main():
