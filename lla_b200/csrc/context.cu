@@ -103,6 +103,8 @@ Context* ctx() {
   cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
   for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  for (auto& row : c->ev_chunk)
+    for (auto& e : row) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   g_ctx[dev].store(c, std::memory_order_release);
   return c;
 }

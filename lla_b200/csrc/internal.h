@@ -60,6 +60,7 @@ struct Context {
   cudaStream_t h2d = nullptr;        // staging streams
   cudaStream_t d2h = nullptr;
   cudaEvent_t ev[12] = {};
+  cudaEvent_t ev_chunk[2][32] = {};  // per column chunk of a blocked update: [0] solve done, [1] product done (lu_blocked)
   cudaStream_t own_stream = nullptr; // the library's stream while a caller-owned one is adopted (llacuda_set_stream)
   // timing of the last host-pointer call (ms): [0]=h2d [1]=compute [2]=d2h [3]=total
   float last_ms[4] = {};

@@ -656,8 +656,8 @@ static int lu_panel_rl(const LuCtx& L, int64_t k, int64_t m, int64_t kb) {
   return 0;
 }
 
-// columns [c0, c1) right of panel (k, kb): interchanges, U12 = L11^-1 A12, A22 -= A21 U12
-static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st, int hint = GEMM_AUTO) {
+// columns [c0, c1) right of panel (k, kb): interchanges and U12 = L11^-1 A12 ...
+static int lu_update_solve(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st) {
   if (c1 <= c0) return 0;
   const int64_t nc = c1 - c0;
   double* A11 = L.A + k + k * L.lda;
@@ -667,10 +667,18 @@ static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int
   if (upd_trace) trace_mark(st, "lu.upd.swp<", k, nc);
   LLA_TRY(dtrsm_left_inv_dev(false, 0, kb, nc, A11, L.lda, L.linv + (k / IB) * IB * IB, A12, L.lda, st));
   if (upd_trace) trace_mark(st, "lu.upd.trsm<", k, nc);
-  if (L.M > k + kb)
-    LLA_TRY(dgemm_dev(0, 0, L.M - k - kb, nc, kb, -1.0, A11 + kb, L.lda, A12, L.lda, 1.0, A12 + kb, L.lda, TRI_FULL, st,
-                      nullptr, hint));
   return 0;
+}
+// ... and A22 -= A21 U12
+static int lu_update_product(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st, int hint = GEMM_AUTO) {
+  if (c1 <= c0 || L.M <= k + kb) return 0;
+  double* A11 = L.A + k + k * L.lda;
+  double* A12 = L.A + k + c0 * L.lda;
+  return dgemm_dev(0, 0, L.M - k - kb, c1 - c0, kb, -1.0, A11 + kb, L.lda, A12, L.lda, 1.0, A12 + kb, L.lda, TRI_FULL, st, nullptr, hint);
+}
+static int lu_update_cols(const LuCtx& L, int64_t k, int64_t kb, int64_t c0, int64_t c1, cudaStream_t st, int hint = GEMM_AUTO) {
+  LLA_TRY(lu_update_solve(L, k, kb, c0, c1, st));
+  return lu_update_product(L, k, kb, c0, c1, st, hint);
 }
 
 // Blocked right-looking driver with one panel of look-ahead: panel k+1 (recursive, cooperative
@@ -716,6 +724,11 @@ static int lu_blocked(LuCtx L) {
   cudaEvent_t ev_b1 = c->ev[10];
   bool have_b1 = false;
   static const bool side_a = getenv("LLACUDA_LU_NO_SIDE_A") == nullptr;
+  static int64_t chunk_w = -1;   // columns per chunk of the pipelined bulk update (0 = off)
+  if (chunk_w < 0) { const char* e = getenv("LLACUDA_LU_CHUNK"); chunk_w = e ? atol(e) : 4096; if (chunk_w % NB) chunk_w = 0; }
+  bool chunk_live[32] = {};      // the chunk's product event has been recorded in this call
+  bool prev_chunked = false;     // the previous step's update recorded per-chunk product events
+  cudaEvent_t ev_t0 = c->ev[11];
   for (int64_t k = 0; k < mn; k += NB) {
     const int64_t kb = (mn - k) < NB ? (mn - k) : NB;
     if (part && !part_on && k > 0 && (L.M - k) <= part_m &&
@@ -804,6 +817,7 @@ static int lu_blocked(LuCtx L) {
     static int reserve = -1;
     if (reserve < 0) { const char* e = getenv("LLACUDA_LU_RESERVE"); reserve = e ? atoi(e) : 0; }  // measured: no gain on B200 (profiles/r01_lu_tuning.txt), off by default
     const bool overlap = (c1 < L.N) && (k + kb < mn);
+    bool step_chunked = false;
     if (ready && k == 0) {
       // first step: the update is separable by column block, so each block starts as soon as its columns are on the device
       for (int64_t cc = c1; cc < L.N; cc += READY_BLOCK) {
@@ -816,17 +830,75 @@ static int lu_blocked(LuCtx L) {
       // signal on their own, so the trailing stream can start while the rest of this update is still running
       int64_t cs = c1;
       const bool next_ext = s2 != s1 && c1 < L.N && (side_a || (ext_m > 0 && (L.M - c0) <= ext_m));
+      // Update-bound phase: the interchanges and the GEMM-only solve of a column chunk (0.95 ms per step over all
+      // columns, low occupancy) run on a stream of their own as soon as the PREVIOUS step's product has left that chunk,
+      // i.e. under the previous step's remaining products; s1 then runs product after product.  Chunks are fixed
+      // absolute column ranges, so one event pair per chunk orders step k - 1's product, step k's solve, step k's product.
+      const bool chunked = chunk_w > 0 && s2 != s1 && !part_on && (L.M - k) > ext_m && L.N / chunk_w < 32;
+      step_chunked = chunked;
+      cudaStream_t sT = c->aux2;
+      // what last wrote the columns of chunk `id`: the previous step's product of that chunk, or its whole update, or nothing
+      auto prev_event = [&](int id) -> cudaEvent_t {
+        if (prev_chunked && chunk_live[id]) return c->ev_chunk[1][id];
+        return have_b ? ev_b : ev_start;
+      };
+      auto solve_chunk = [&](int64_t lo, int64_t hi) -> int {     // on sT, after the previous product of these columns
+        const int id = (int)(lo / chunk_w);
+        LLA_CUDA(cudaStreamWaitEvent(sT, ev_panel, 0));
+        LLA_CUDA(cudaStreamWaitEvent(sT, prev_event(id), 0));
+        LLA_TRY(lu_update_solve(L, k, kb, lo, hi, sT));
+        LLA_CUDA(cudaEventRecord(c->ev_chunk[0][id], sT));
+        return 0;
+      };
+      auto product_chunk = [&](int64_t lo, int64_t hi) -> int {   // on s1, after the solve of these columns
+        const int id = (int)(lo / chunk_w);
+        LLA_CUDA(cudaStreamWaitEvent(s1, c->ev_chunk[0][id], 0));
+        LLA_TRY(lu_update_product(L, k, kb, lo, hi, s1));
+        LLA_CUDA(cudaEventRecord(c->ev_chunk[1][id], s1));
+        chunk_live[id] = true;
+        return 0;
+      };
       if (next_ext) {
         cs = c1 + NB < L.N ? c1 + NB : L.N;
-        LLA_TRY(lu_update_cols(L, k, kb, c1, cs, s1));
+        if (chunked) {
+          // the first piece lies inside one chunk; its product is recorded in ev_b1, the chunk's event follows below
+          const int id = (int)(c1 / chunk_w);
+          LLA_CUDA(cudaStreamWaitEvent(sT, ev_panel, 0));
+          LLA_CUDA(cudaStreamWaitEvent(sT, prev_event(id), 0));
+          LLA_TRY(lu_update_solve(L, k, kb, c1, cs, sT));
+          LLA_CUDA(cudaEventRecord(ev_t0, sT));
+          LLA_CUDA(cudaStreamWaitEvent(s1, ev_t0, 0));
+          LLA_TRY(lu_update_product(L, k, kb, c1, cs, s1));
+        } else {
+          LLA_TRY(lu_update_cols(L, k, kb, c1, cs, s1));
+        }
         LLA_CUDA(cudaEventRecord(ev_b1, s1));
         have_b1 = true;
       }
-      LLA_TRY(lu_update_cols(L, k, kb, cs, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
+      if (chunked) {
+        for (int64_t lo = cs; lo < L.N;) {
+          const int64_t hi = (lo / chunk_w + 1) * chunk_w < L.N ? (lo / chunk_w + 1) * chunk_w : L.N;
+          LLA_TRY(solve_chunk(lo, hi));
+          lo = hi;
+        }
+        for (int64_t lo = cs; lo < L.N;) {
+          const int64_t hi = (lo / chunk_w + 1) * chunk_w < L.N ? (lo / chunk_w + 1) * chunk_w : L.N;
+          LLA_TRY(product_chunk(lo, hi));
+          lo = hi;
+        }
+        // a chunk that the first piece cut (its columns [c1, cs) were updated outside the loop) is covered by s1's order
+        if (cs > c1 && cs % chunk_w != 0 && cs >= L.N) {
+          LLA_CUDA(cudaEventRecord(c->ev_chunk[1][(int)(c1 / chunk_w)], s1));
+          chunk_live[(int)(c1 / chunk_w)] = true;
+        }
+      } else {
+        LLA_TRY(lu_update_cols(L, k, kb, cs, L.N, s1, (overlap && reserve >= 8) ? GEMM_RESERVE_SMS + (reserve - 8) : GEMM_AUTO));
+      }
     }
     trace_mark(s1, "lu.updB<", k, L.N - c1);
     LLA_CUDA(cudaEventRecord(ev_b, s1));
     have_b = true;
+    prev_chunked = step_chunked;
     if (join_a) LLA_CUDA(cudaStreamWaitEvent(s1, ev_a, 0));
     // rows [k, k+kb) are final: U12 was solved at the head of this update, the L part received its last
     // interchanges from this panel (later panels only touch rows below)
