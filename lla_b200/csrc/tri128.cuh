@@ -141,58 +141,102 @@ __device__ __forceinline__ void tri128_store(const double* S, double* __restrict
   }
 }
 
+// One warp factors the 32 x 32 diagonal block at (c0, c0) of S in registers (lane = row) and leaves 1 / l_kk in
+// rdiag[c0 ..].  Column k of L travels through shared memory: every lane stores its l_ik, everybody reads the l_ck it
+// needs back as 16-byte broadcasts (one LSU instruction per two columns where a 64-bit shuffle costs two per column);
+// the next pivot's reciprocal square root is in flight while the remaining columns of the current step update.
+// lbuf: 2 x 32 doubles (double-buffered by the parity of k, so one __syncwarp per pivot).  Returns 0 or c0 + k + 1.
+__device__ __forceinline__ int potrf32_diag_warp(double* S, int c0, double* rdiag, double* lbuf, int lane) {
+  double a[32];
+  double* D = S + (c0 + lane) + c0 * T128_SP;  // row c0 + lane
+#pragma unroll
+  for (int c = 0; c < 32; c++) a[c] = D[c * T128_SP];
+  int fail = 0;
+  double dmine = 1.0;  // lane k keeps d_k; its square root is taken once, after the loop
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  double rs = rsqrt(d);
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    if (!(d > 0.0)) { fail = c0 + k + 1; break; }
+    if (lane == k) dmine = d;
+    if (lane == 0) rdiag[c0 + k] = rs;
+    const double l = a[k] * rs;
+    a[k] = l;
+    double dn = 1.0, rsn = 1.0;
+    if (k + 1 < 32) {
+      double* lb = lbuf + (k & 1) * 32;
+      lb[lane] = l;
+      // next pivot first, without waiting for the broadcast: lane k + 1 needs only its own l for d_{k+1} = a - l * l;
+      // its reciprocal square root is in flight under the updates of the other columns
+      dn = __shfl_sync(0xffffffffu, fma(-l, l, a[k + 1]), k + 1);
+      rsn = rsqrt(dn);
+      __syncwarp();
+      a[k + 1] = fma(-l, lb[k + 1], a[k + 1]);
+      int c = k + 2;
+      if (c < 32 && (c & 1)) { a[c] = fma(-l, lb[c], a[c]); c++; }
+#pragma unroll
+      for (; c < 32; c += 2) {  // meaningful for rows >= c only
+        const double2 v = *reinterpret_cast<const double2*>(lb + c);
+        a[c] = fma(-l, v.x, a[c]);
+        a[c + 1] = fma(-l, v.y, a[c + 1]);
+      }
+    }
+    d = dn; rs = rsn;
+  }
+  if (fail) return fail;
+  const double diag = sqrt(dmine);  // the diagonal itself (lane k's a[k] holds d_k * rs, a rounding away from it)
+#pragma unroll
+  for (int c = 0; c < 32; c++)
+    if (c <= lane) D[c * T128_SP] = (c == lane) ? diag : a[c];
+  return 0;
+}
+
+// Rank-32 update S[i0.., j0..] -= sum_k S[i0.., c0 + k] S[j0.., c0 + k] of one 4 x 4 tile of the lower triangle
+// (entries above the diagonal of a diagonal tile are left alone).  i0, j0 are multiples of 4: 16-byte loads.
+__device__ __forceinline__ void potrf128_tile_update(double* S, int c0, int i0, int j0) {
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < 32; k++) {
+    const double2* ap = reinterpret_cast<const double2*>(S + i0 + (c0 + k) * T128_SP);
+    const double2* bp = reinterpret_cast<const double2*>(S + j0 + (c0 + k) * T128_SP);
+    const double2 a01 = ap[0], a23 = ap[1], b01 = bp[0], b23 = bp[1];
+    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int v = 0; v < 4; v++) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+      if (i0 + u >= j0 + v) S[i0 + u + (j0 + v) * T128_SP] -= acc[u][v];
+}
+
 // In-place lower Cholesky S = L L^T of the leading r x r block (S is identity-padded to 128 x 128),
-// right-looking over 32-column block steps:
-//   (1) warp 0 factors the 32 x 32 diagonal block in registers (lane = row; the pivot column travels by
-//       shuffles, the reciprocal square root of the next pivot is in flight while the current column's
-//       updates issue) and leaves 1 / l_kk in rdiag;
-//   (2) one thread per row below solves its row against L11^T by substitution (L11 read as broadcasts);
-//   (3) the whole CTA applies the rank-32 update to the lower triangle of the trailing block, 4 x 4
-//       register tiles enumerated over the triangle only.
+// right-looking over 32-column block steps with the diagonal factorisations off the critical path:
+//   (1) one thread per row below the block solves its row against L11^T by substitution (L11 read as broadcasts);
+//   (2) the rank-32 update of the NEXT diagonal block (36 tiles of 4 x 4);
+//   (3) warp 0 factors that next diagonal block in registers (potrf32_diag_warp) WHILE the other 15 warps apply the
+//       rank-32 update to the rest of the trailing block (tiles enumerated over the trapezoid below it).
 // Returns 0, or k+1 for the first non-positive / NaN pivot (uniform across the CTA).  rdiag: 128 doubles.
 __device__ __forceinline__ int potrf128_lower_smem(double* S, double* rdiag, int r, int tid) {
   __shared__ int s_fail;
+  __shared__ __align__(16) double s_lbuf[64];
   const int lane = tid & 31, warp = tid >> 5;
   if (tid < 128) rdiag[tid] = 1.0;
   if (tid == 0) s_fail = 0;
   __syncthreads();
+  if (warp == 0) {
+    const int fail = potrf32_diag_warp(S, 0, rdiag, s_lbuf, lane);
+    if (fail && lane == 0) s_fail = fail;
+  }
+  __syncthreads();
   for (int c0 = 0; c0 < r; c0 += 32) {
-    if (warp == 0) {
-      double a[32];
-      double* D = S + (c0 + lane) + c0 * T128_SP;  // row c0 + lane
-#pragma unroll
-      for (int c = 0; c < 32; c++) a[c] = D[c * T128_SP];
-      int fail = 0;
-      double dmine = 1.0;  // lane k keeps d_k; its square root is taken once, after the loop
-      double d = __shfl_sync(0xffffffffu, a[0], 0);
-      double rs = rsqrt(d);
-#pragma unroll
-      for (int k = 0; k < 32; k++) {
-        if (!(d > 0.0)) { fail = c0 + k + 1; break; }
-        if (lane == k) dmine = d;
-        if (lane == 0) rdiag[c0 + k] = rs;
-        const double l = a[k] * rs;
-        a[k] = l;
-        double dn = 1.0, rsn = 1.0;
-        if (k + 1 < 32) {  // next pivot first: its reciprocal square root is in flight under the remaining updates
-          a[k + 1] = fma(-l, __shfl_sync(0xffffffffu, l, k + 1), a[k + 1]);
-          dn = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
-          rsn = rsqrt(dn);
-        }
-#pragma unroll
-        for (int c = k + 2; c < 32; c++) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);  // meaningful for rows >= c only
-        d = dn; rs = rsn;
-      }
-      const double diag = sqrt(dmine);  // the diagonal itself (lane k's a[k] holds d_k * rs, a rounding away from it)
-      if (fail) {
-        if (lane == 0) s_fail = fail;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; c++)
-          if (c <= lane) D[c * T128_SP] = (c == lane) ? diag : a[c];
-      }
-    }
-    __syncthreads();
     if (s_fail) return s_fail;
     const int t0 = c0 + 32;          // first row / column of the trailing block
     const int nbelow = T128 - t0;
@@ -206,46 +250,45 @@ __device__ __forceinline__ int potrf128_lower_smem(double* S, double* rdiag, int
 #pragma unroll
       for (int k = 0; k < 32; k++) {
         x[k] *= rdiag[c0 + k];
+        const double* col = L11 + k * T128_SP;   // column k of L11: 16-byte aligned (pitch 130, c0 a multiple of 32)
+        int c = k + 1;
+        if (c < 32 && (c & 1)) { x[c] = fma(-x[k], col[c], x[c]); c++; }
 #pragma unroll
-        for (int c = k + 1; c < 32; c++) x[c] = fma(-x[k], L11[c + k * T128_SP], x[c]);
+        for (; c < 32; c += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(col + c);
+          x[c] = fma(-x[k], v.x, x[c]);
+          x[c + 1] = fma(-x[k], v.y, x[c + 1]);
+        }
       }
 #pragma unroll
       for (int c = 0; c < 32; c++) R[c * T128_SP] = x[c];
     }
     __syncthreads();
-    // trailing block: tiles (ti >= tj) of the T x T tile triangle, folded into a (T/2) x (T+1) rectangle
-    const int T = nbelow / 4;
-    for (int t = tid; t < (T / 2) * (T + 1); t += T128_THREADS) {
-      const int pp = t / (T + 1), qq = t % (T + 1);
-      int ti, tj;
-      if (qq <= T / 2 + pp) { ti = T / 2 + pp; tj = qq; }
-      else { ti = T / 2 - 1 - pp; tj = qq - (T / 2 + pp + 1); }
-      const int i0 = t0 + 4 * ti, j0 = t0 + 4 * tj;  // 16-byte aligned: rows are loaded as two double2 each
-      double acc[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < 32; k++) {
-        const double2* ap = reinterpret_cast<const double2*>(S + i0 + (c0 + k) * T128_SP);
-        const double2* bp = reinterpret_cast<const double2*>(S + j0 + (c0 + k) * T128_SP);
-        const double2 a01 = ap[0], a23 = ap[1], b01 = bp[0], b23 = bp[1];
-        const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int v = 0; v < 4; v++) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+    // the next diagonal block first: tiles (ti >= tj) of its 8 x 8 tile triangle
+    if (tid < 36) {
+      int ti = 0, t = tid;
+      while (t > ti) { t -= ti + 1; ti++; }
+      potrf128_tile_update(S, c0, t0 + 4 * ti, t0 + 4 * t);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (t0 < r) {   // beyond r the block is identity padding
+        const int fail = potrf32_diag_warp(S, t0, rdiag, s_lbuf, lane);
+        if (fail && lane == 0) s_fail = fail;
       }
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++)
-          if (i0 + u >= j0 + v) S[i0 + u + (j0 + v) * T128_SP] -= acc[u][v];
+    } else {
+      // rows t0 + 32 .. 127 of the trailing block: tile rows ti = 8 .. T - 1, tile columns 0 .. ti
+      const int T = nbelow / 4;
+      const int count = (T * (T + 1)) / 2 - 36;
+      for (int q = tid - 32; q < count; q += T128_THREADS - 32) {
+        int ti = 8, t = q;
+        while (t > ti) { t -= ti + 1; ti++; }
+        potrf128_tile_update(S, c0, t0 + 4 * ti, t0 + 4 * t);
+      }
     }
     __syncthreads();
   }
-  return 0;
+  return s_fail;
 }
 
 }  // namespace llacuda
