@@ -776,10 +776,12 @@ def main():
             h2d = 2 * n * n * 8 + (n * n * 8 + world * n * NRHS * 8) + tri
             d2h = n * n * 8 + (n * n * 8 + n * NRHS * 8 + n * 4 + 4) + (tri + 4)
             e2e = {"value": ep["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "steps": steps, "host_memory": "pageable (plain NumPy arrays, what LLA's with-pinned-objects yields), staged by "
+                   "steps": steps, "warmup": ep["warmup"], "per_step_ms_mm_solve_cholesky": ep["per_step_ms_mm_solve_cholesky"],
+                   "host_memory": "pageable (plain NumPy arrays, what LLA's with-pinned-objects yields), staged by "
                    "the library's pinned ring (csrc/hostpipe.cu)", "ops": ep["ops"], "entry_points": ep["entry_points"],
                    "solve_scaled_residual": ep["solve_scaled_residual"],
-                   "pinned": {"value": pin["value"], "ops": pin["ops"], "host_memory": "page-locked (llacuda_host_alloc)"},
+                   "pinned": {"value": pin["value"], "ops": pin["ops"], "host_memory": "page-locked (llacuda_host_alloc)",
+                              "per_step_ms_mm_solve_cholesky": pin["per_step_ms_mm_solve_cholesky"]},
                    "pageable_over_pinned": ep["value"] / pin["value"]}
             if world > 1:
                 PD.finalize()
