@@ -119,6 +119,18 @@ const SmPartition* sm_partition() {
   if (P.tried) return P.ok ? &P : nullptr;
   P.tried = true;
   if (getenv("LLACUDA_NO_PARTITION")) return nullptr;
+  // Nsight Compute cannot prepare a cooperative launch on a green-context stream ("Failed to prepare kernel for
+  // profiling", and it then shuts the application down): under its injection library the drivers keep their priority
+  // streams (measured cost of that: 1-2 % of dgetrf)
+  if (FILE* f = fopen("/proc/self/maps", "r")) {
+    char line[512];
+    bool profiled = false;
+    while (!profiled && fgets(line, sizeof line, f))
+      profiled = strstr(line, "libcuda-injection") != nullptr || strstr(line, "nsight-compute") != nullptr ||
+                 strstr(line, "nsight_compute") != nullptr;
+    fclose(f);
+    if (profiled) return nullptr;
+  }
   int want = 24;   // 3 panel CTAs of 128 rows per SM: LU panels up to 9216 rows fit (measured: profiles/r02_sm_partition.md)
   if (const char* e = getenv("LLACUDA_PANEL_SMS")) want = atoi(e);
   if (want < 8) return nullptr;
