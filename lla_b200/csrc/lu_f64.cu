@@ -493,6 +493,7 @@ struct LuCtx {
   cudaStream_t st;
   int per_sm = 1;            // co-resident panel CTAs per SM (occupancy of the leaf kernel)
   struct LuExt* ext = nullptr;   // chain-bound phase: the next panel's columns trail this panel block by block
+  int pr = 0;                    // rows per CTA of the panel kernel for this panel (0 = panel_rows())
 };
 
 // The columns [c0, c1) of the NEXT panel, updated on stream `sx` one 128-column block behind the panel chain (see
@@ -560,7 +561,7 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   }
   static const bool leaf_trace = getenv("LLACUDA_TRACE_LEAF") != nullptr;
   if (leaf_trace) trace_mark(L.st, "lu.leaf>", j0, m);
-  const int pr = panel_rows();
+  const int pr = L.pr ? L.pr : panel_rows();
   if (pr == 128) LLA_TRY(launch_panel<128>(L, P, m, w, j0, epoch, dbg));
   else if (pr == 256) LLA_TRY(launch_panel<256>(L, P, m, w, j0, epoch, dbg));
   else LLA_TRY(launch_panel<512>(L, P, m, w, j0, epoch, dbg));
@@ -762,6 +763,12 @@ static int lu_blocked(LuCtx L) {
       else if (have_b) LLA_CUDA(cudaStreamWaitEvent(X.sx, ev_b, 0));
       P.ext = &X;
     }
+    // update-bound phase: 256-row panel CTAs -- half as many CTAs taking register file and shared memory from the
+    // update's GEMM CTAs on half as many SMs; the panel itself is hidden there (LLACUDA_LU_PR_EARLY = 0 | 256 | 512;
+    // dgetrf n = 16384: 138.3 / 136.3 / 137.4 ms)
+    static int pr_early = -1;
+    if (pr_early < 0) { const char* e = getenv("LLACUDA_LU_PR_EARLY"); pr_early = e ? atoi(e) : 256; if (pr_early != 256 && pr_early != 512) pr_early = 0; }
+    if (pr_early && (L.M - k) > ext_m && !part_on) P.pr = pr_early;
     if (ready && k == 0) LLA_TRY(ready->fn(ready->user, 0, kb, s2));
     trace_mark(s2, "lu.panel>", k, kb);
     static const bool panel_rl = getenv("LLACUDA_LU_PANEL_RL") != nullptr;
