@@ -100,6 +100,7 @@ Context* ctx() {
   cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, hi);  // panels ahead of trailing updates
   cudaStreamCreateWithPriority(&c->aux2, cudaStreamNonBlocking, hi);
   cudaStreamCreateWithPriority(&c->aux3, cudaStreamNonBlocking, hi);
+  cudaStreamCreateWithPriority(&c->aux4, cudaStreamNonBlocking, lo);
   cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
   for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -191,6 +192,7 @@ void drain_streams() {
   cudaStreamSynchronize(c->aux);
   cudaStreamSynchronize(c->aux2);
   cudaStreamSynchronize(c->aux3);
+  cudaStreamSynchronize(c->aux4);
   cudaStreamSynchronize(c->h2d);
   cudaStreamSynchronize(c->d2h);
   if (g_part[dev].ok) {
@@ -340,6 +342,7 @@ int llacuda_synchronize(void) {
   LLA_CUDA(cudaStreamSynchronize(c->aux));
   LLA_CUDA(cudaStreamSynchronize(c->aux2));
   LLA_CUDA(cudaStreamSynchronize(c->aux3));
+  LLA_CUDA(cudaStreamSynchronize(c->aux4));
   return 0;
 }
 

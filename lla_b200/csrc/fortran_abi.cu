@@ -434,14 +434,13 @@ static int dgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ipi
   tm.mark(1);
   RowSender rs;
   LLA_TRY(rs.arm(sa, a, lda, cx->d2h, false));
-  int rc = dgetrf_dev(n, n, sa.ptr<double>(), sa.ld, (int*)piv.p, (int*)inf.p, st);
+  // DGESV solves only when the factorisation reported INFO = 0: the forward substitution rides along with the
+  // factorisation, the back substitution is gated by the INFO word and B is restored when it is not zero
+  int rc = dgesv_dev(n, nrhs, sa.ptr<double>(), sa.ld, (int*)piv.p, sb.ptr<double>(), sb.ld, (int*)inf.p, st);
   rs.disarm();
   up.disarm();
   LLA_TRY(rc);
   LLA_TRY(up.finish(st));
-  // DGESV solves only when the factorisation reported INFO = 0: the INFO word is the abort flag
-  LLA_TRY(dgetrs_dev(0, n, nrhs, sa.ptr<double>(), sa.ld, (const int*)piv.p, sb.ptr<double>(), sb.ld, st,
-                     (const int*)inf.p));
   tm.mark(2);
   LLA_TRY(stage_download_rows(sa, a, lda, rs.sent_upto, n, 0, st));
   LLA_CUDA(cudaStreamSynchronize(cx->d2h));
@@ -620,8 +619,7 @@ LLA_EXPORT int llacuda_dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda
   Context* cx = ctx();
   if (!cx) return LLACUDA_ERR_NO_DEVICE;
   if (n < 0 || nrhs < 0 || lda < max1(n) || ldb < max1(n)) return LLACUDA_ERR_BAD_ARG;
-  LLA_TRY(dgetrf_dev(n, n, A, lda, ipiv_dev, info_dev, cx->stream));
-  return dgetrs_dev(0, n, nrhs, A, lda, ipiv_dev, B, ldb, cx->stream, info_dev);
+  return dgesv_dev(n, nrhs, A, lda, ipiv_dev, B, ldb, info_dev, cx->stream);
 }
 LLA_EXPORT int llacuda_dpotrf_dev(char uplo, int64_t n, double* A, int64_t lda, int* info_dev) {
   ApiLock api_lock;
@@ -1039,10 +1037,8 @@ LLA_EXPORT void llacuda_dgesv_rm(const fint* n_, const fint* nrhs_, const double
     LLA_TRY(inf.alloc(sizeof(int)));
     LLA_TRY(A.upload(n, n, a, lda, st));
     LLA_TRY(B.upload(n, nrhs, b, ldb, st));
-    LLA_TRY(dgetrf_dev(n, n, A.cm.ptr<double>(), A.cm.ld, (int*)piv.p, (int*)inf.p, st));
-    LLA_TRY(dgetrs_dev(0, n, nrhs, A.cm.ptr<double>(), A.cm.ld, (const int*)piv.p, B.cm.ptr<double>(), B.cm.ld, st,
-                       (const int*)inf.p));
-    LLA_TRY(B.download(n, nrhs, b, ldb, st));   // untouched B comes back when INFO > 0 (the solve was skipped)
+    LLA_TRY(dgesv_dev(n, nrhs, A.cm.ptr<double>(), A.cm.ld, (int*)piv.p, B.cm.ptr<double>(), B.cm.ld, (int*)inf.p, st));
+    LLA_TRY(B.download(n, nrhs, b, ldb, st));   // untouched B comes back when INFO > 0 (restored / the solve was skipped)
     IntOut inf_out(info, 1);
     LLA_CUDA(cudaMemcpyAsync(inf_out.host32(), inf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     LLA_TRY(stage_sync(st));

@@ -55,11 +55,12 @@ struct Context {
   int sm_count = 0;
   cudaStream_t stream = nullptr;     // main compute stream
   cudaStream_t aux = nullptr;        // panel / look-ahead stream
+  cudaStream_t aux4 = nullptr;       // normal priority: right-hand sides riding along with a factorisation
   cudaStream_t aux3 = nullptr;       // third high-priority stream: the part of a block row the panel chain needs next
   cudaStream_t aux2 = nullptr;       // second high-priority stream: block-row solves beside the trailing update
   cudaStream_t h2d = nullptr;        // staging streams
   cudaStream_t d2h = nullptr;
-  cudaEvent_t ev[12] = {};
+  cudaEvent_t ev[16] = {};
   cudaEvent_t ev_chunk[2][32] = {};  // per column chunk of a blocked update: [0] solve done, [1] product done (lu_blocked)
   cudaStream_t own_stream = nullptr; // the library's stream while a caller-owned one is adopted (llacuda_set_stream)
   // timing of the last host-pointer call (ms): [0]=h2d [1]=compute [2]=d2h [3]=total
@@ -190,7 +191,14 @@ const RangeReadyHook* range_ready_hook();
 constexpr int64_t READY_BLOCK = 2048;                  // granularity the drivers announce ranges in
 void set_rows_final_hook(const RowsFinalHook* h);   // nullptr clears; valid for the next dgetrf_dev / dpotrf_dev only
 const RowsFinalHook* rows_final_hook();
-int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st);
+// Right-hand sides that ride along with a blocked factorisation: after each panel its interchanges, the solve with the
+// panel's unit-lower triangle and the product with the rows below are applied to B on a side stream, so that when
+// dgetrf_dev returns B holds L^-1 P B and only the back substitution is left.  `done` tells whether the driver took the
+// rider (the unblocked path for small orders does not).
+struct LuRhs { double* B = nullptr; int64_t ldb = 0, nrhs = 0; bool done = false; };
+int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st, LuRhs* rhs = nullptr);
+// DGESV on device pointers: factorisation with the right-hand sides riding along, back substitution, B restored when INFO > 0
+int dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv, double* B, int64_t ldb, int* info_dev, cudaStream_t st);
 // rows i in [k1,k2) swapped with ipiv[i]-1 (1-based LAPACK pivots), forward or backward order
 int dlaswp_dev(int64_t ncols, double* A, int64_t lda, int64_t k1, int64_t k2, const int* ipiv,
                bool forward, cudaStream_t st, const int* abort_flag = nullptr);

@@ -494,6 +494,7 @@ struct LuCtx {
   int per_sm = 1;            // co-resident panel CTAs per SM (occupancy of the leaf kernel)
   struct LuExt* ext = nullptr;   // chain-bound phase: the next panel's columns trail this panel block by block
   int pr = 0;                    // rows per CTA of the panel kernel for this panel (0 = panel_rows())
+  LuRhs* rhs = nullptr;          // right-hand sides riding along (blocked driver only)
 };
 
 // The columns [c0, c1) of the NEXT panel, updated on stream `sx` one 128-column block behind the panel chain (see
@@ -696,12 +697,14 @@ static int lu_blocked(LuCtx L) {
   if (mn <= 2 * NB) {
     if (ready) LLA_TRY(ready->fn(ready->user, 0, L.N, L.st));
     L.swap_c0 = 0; L.swap_c1 = L.N;
+    L.rhs = nullptr;   // no rider here: the caller solves
     return lu_rec(L, 0, L.M, L.N);
   }
   cudaStream_t s1 = L.st, s2 = c->aux, s3 = c->h2d;
   cudaEvent_t ev_start = c->ev[3], ev_panel = c->ev[4], ev_a = c->ev[5], ev_b = c->ev[6], ev_left = c->ev[7];
   LLA_CUDA(cudaEventRecord(ev_start, s1));
   LLA_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+  if (L.rhs) LLA_CUDA(cudaStreamWaitEvent(c->aux4, ev_start, 0));
   // Chain-bound phase: the panel chain (cooperative leaves, interchanges, small solves and products) moves to its own SM
   // partition, the trailing update to the rest.  Under a concurrent update on shared SMs a panel takes 2-3x as long as
   // alone (profiles/r01b_trace_dgetrf_16384_leaves.log: leaves 155 us against 83), and from the step where the update is
@@ -729,7 +732,7 @@ static int lu_blocked(LuCtx L) {
   if (chunk_w < 0) { const char* e = getenv("LLACUDA_LU_CHUNK"); chunk_w = e ? atol(e) : 4096; if (chunk_w % NB) chunk_w = 0; }
   bool chunk_live[32] = {};      // the chunk's product event has been recorded in this call
   bool prev_chunked = false;     // the previous step's update recorded per-chunk product events
-  cudaEvent_t ev_t0 = c->ev[11];
+  cudaEvent_t ev_t0 = c->ev[11], ev_rhs = c->ev[12];
   for (int64_t k = 0; k < mn; k += NB) {
     const int64_t kb = (mn - k) < NB ? (mn - k) : NB;
     if (part && !part_on && k > 0 && (L.M - k) <= part_m &&
@@ -776,10 +779,24 @@ static int lu_blocked(LuCtx L) {
     else LLA_TRY(lu_rec(P, k, L.M - k, kb));
     trace_mark(s2, "lu.panel<", k, kb);
     LLA_CUDA(cudaEventRecord(ev_panel, s2));
+    if (L.rhs) {
+      // the right-hand sides ride along: interchanges of this panel, solve with its unit-lower triangle, rows below
+      LuRhs& Rh = *L.rhs;
+      cudaStream_t sB = c->aux4;
+      double* A11 = L.A + k + k * L.lda;
+      LLA_CUDA(cudaStreamWaitEvent(sB, ev_panel, 0));
+      LLA_TRY(dlaswp_dev(Rh.nrhs, Rh.B, Rh.ldb, k, k + kb, L.ipiv, true, sB));
+      LLA_TRY(dtrsm_left_inv_dev(false, 0, kb, Rh.nrhs, A11, L.lda, L.linv + (k / IB) * IB * IB, Rh.B + k, Rh.ldb, sB));
+      if (L.M > k + kb)
+        LLA_TRY(dgemm_dev(0, 0, L.M - k - kb, Rh.nrhs, kb, -1.0, A11 + kb, L.lda, Rh.B + k, Rh.ldb, 1.0, Rh.B + k + kb, Rh.ldb, TRI_FULL, sB));
+      LLA_CUDA(cudaEventRecord(ev_rhs, sB));   // the left interchanges of later steps permute the rows this product reads
+      Rh.done = true;
+    }
     // ---- interchanges of the finished columns [0, k) on s3 (after the update that still reads them)
     if (k > 0) {
       LLA_CUDA(cudaStreamWaitEvent(s3, ev_panel, 0));
       if (have_b) LLA_CUDA(cudaStreamWaitEvent(s3, ev_b, 0));
+      if (L.rhs) LLA_CUDA(cudaStreamWaitEvent(s3, ev_rhs, 0));
       LLA_TRY(dlaswp_dev(k, L.A, L.lda, k, k + kb, L.ipiv, true, s3));
       LLA_CUDA(cudaEventRecord(ev_left, s3));
     }
@@ -913,6 +930,7 @@ static int lu_blocked(LuCtx L) {
   }
   LLA_CUDA(cudaStreamWaitEvent(s1, ev_panel, 0));
   if (mn > NB) LLA_CUDA(cudaStreamWaitEvent(s1, ev_left, 0));
+  if (L.rhs) LLA_CUDA(cudaStreamWaitEvent(s1, ev_rhs, 0));
   if (part_on) {   // back to the caller's stream
     LLA_CUDA(cudaEventRecord(ev_start, s1));
     LLA_CUDA(cudaStreamWaitEvent(L.st, ev_start, 0));
@@ -920,7 +938,7 @@ static int lu_blocked(LuCtx L) {
   return 0;
 }
 
-int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st) {
+int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* info_dev, cudaStream_t st, LuRhs* rhs) {
   Context* c = ctx();
   if (!c) return LLACUDA_ERR_NO_DEVICE;
   LLA_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
@@ -953,6 +971,7 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
   L.A = A; L.lda = lda; L.M = m; L.N = n; L.ipiv = ipiv; L.info = info_dev; L.st = st;
   L.swap_c0 = 0; L.swap_c1 = n;
   L.per_sm = per_sm;
+  L.rhs = (rhs && rhs->B && rhs->nrhs > 0 && m == n) ? rhs : nullptr;
   L.hdrs = (PanelHdr*)ar.take(sizeof(PanelHdr) * 2 * maxG);
   L.rows = (PanelRow*)ar.take(sizeof(PanelRow) * 2 * maxG);
   L.rowj = (PanelRow*)ar.take(sizeof(PanelRow) * 2);
@@ -980,6 +999,46 @@ int dgetrs_dev(int op, int64_t n, int64_t nrhs, const double* A, int64_t lda, co
     LLA_TRY(dtrsm_left_inv_dev(false, 1, n, nrhs, A, lda, linv, B, ldb, st, abort_flag));
     LLA_TRY(dlaswp_dev(nrhs, B, ldb, 0, n, ipiv, false, st, abort_flag));
   }
+  return 0;
+}
+
+// B <- saved copy when the factorisation reported INFO != 0 (DGESV leaves B alone then)
+__global__ void lla_restore_rhs_kernel(const int* __restrict__ info, double* __restrict__ B, int64_t ldb,
+                                       const double* __restrict__ save, int64_t n, int64_t nrhs) {
+  if (*info == 0) return;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * nrhs; idx += (int64_t)gridDim.x * blockDim.x)
+    B[idx % n + (idx / n) * ldb] = save[idx];
+}
+
+int dgesv_dev(int64_t n, int64_t nrhs, double* A, int64_t lda, int* ipiv, double* B, int64_t ldb, int* info_dev, cudaStream_t st) {
+  static const bool no_rider = getenv("LLACUDA_LU_NO_RHS_RIDER") != nullptr;
+  if (n <= 0) return dgetrf_dev(n, n, A, lda, ipiv, info_dev, st);
+  if (nrhs <= 0 || nrhs > 1024 || no_rider) {
+    LLA_TRY(dgetrf_dev(n, n, A, lda, ipiv, info_dev, st));
+    return dgetrs_dev(0, n, nrhs, A, lda, ipiv, B, ldb, st, info_dev);
+  }
+  // the forward substitution rides along with the factorisation (one panel behind it, on a side stream); a copy of B
+  // is kept for the singular case, in which DGESV does not touch B
+  Context* c = ctx();
+  if (!c) return LLACUDA_ERR_NO_DEVICE;
+  // keyed by the rider's stream: the factorisation's own arena is the scratch of `st`
+  double* save = (double*)stream_scratch(c->aux4, (size_t)n * nrhs * sizeof(double));
+  if (!save) { set_error(__FILE__, __LINE__, "dgesv: out of device memory for the right-hand-side copy", (int)n); return LLACUDA_ERR_CUDA_BASE; }
+  LLA_CUDA(cudaMemcpy2DAsync(save, (size_t)n * 8, B, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyDeviceToDevice, st));
+  LuRhs rider;
+  rider.B = B; rider.ldb = ldb; rider.nrhs = nrhs;
+  LLA_TRY(dgetrf_dev(n, n, A, lda, ipiv, info_dev, st, &rider));
+  if (!rider.done) return dgetrs_dev(0, n, nrhs, A, lda, ipiv, B, ldb, st, info_dev);
+  {
+    Arena ar;
+    LLA_TRY(ar.reserve(tinv_bytes(n) + 1024, st));
+    double* uinv = (double*)ar.take(tinv_bytes(n));
+    LLA_TRY(dtrtri_blocks_dev(true, false, n, A, lda, uinv, st, info_dev));
+    LLA_TRY(dtrsm_left_inv_dev(true, 0, n, nrhs, A, lda, uinv, B, ldb, st, info_dev));
+  }
+  lla_restore_rhs_kernel<<<256, 256, 0, st>>>(info_dev, B, ldb, save, n, nrhs);
+  count_launch();
+  LLA_CUDA(cudaGetLastError());
   return 0;
 }
 
