@@ -302,8 +302,7 @@ def gpu_value_leg(args, rank, world, local_rank, ctl):
             PD.set_grid(Pl, Ql)
 
             def solve():
-                infos.append(PD.pdgetrf_local(n, DIST_NB, W_l.data_ptr(), n // Pl, ipiv.data_ptr()))
-                PD.pdgetrs_local(n, DIST_NB, W_l.data_ptr(), n // Pl, ipiv.data_ptr(), X.data_ptr(), n, nrhs)
+                infos.append(PD.pdgesv_local(n, DIST_NB, W_l.data_ptr(), n // Pl, ipiv.data_ptr(), X.data_ptr(), n, nrhs))
             ms_solve = timed_call(solve, dstream)
             W_c.copy_(S_c)
             PD.set_grid(Pc, Qc)

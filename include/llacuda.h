@@ -372,6 +372,10 @@ int  llacuda_pdpotrf_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* 
 int  llacuda_pdgetrf_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv_dev, int* info);
 int  llacuda_pdgetrs_local(int64_t Np, int64_t nb, const double* LU, int64_t lld, const int* ipiv_dev, double* B, int64_t ldb,
                            int64_t nrhs);                                                         /* B replicated */
+/* DGESV in one call (reference call site src/linear-algebra.lisp:282-289): on block columns the forward substitution
+   rides along with the factorisation; B (replicated) holds X when *info == 0 and is not meaningful otherwise */
+int  llacuda_pdgesv_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv_dev, double* B, int64_t ldb, int64_t nrhs,
+                          int* info);
 int  llacuda_pdpotrs_local(int64_t Np, int64_t nb, const double* U, int64_t lld, double* B, int64_t ldb, int64_t nrhs);
 /* ownership arithmetic of the layout (pure functions) */
 int64_t llacuda_dist_numroc(int64_t n, int64_t nb, int iproc, int nprocs);

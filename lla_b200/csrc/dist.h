@@ -88,7 +88,11 @@ int summa_rank(Rank& R, int64_t Mp, int64_t Np, int64_t Kp, int64_t nb, T alpha,
 // INFO (LAPACK's, global index) lands in R.dflag[0] on every rank
 int pdpotrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld);
 // P A = L U with partial pivoting; ipiv: device int32[Np], LAPACK's global 1-based swap sequence, on every rank
-int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv);
+// B (Np x nrhs, ldb, replicated on every rank), optional: on a 1 x Q grid the right-hand sides ride along with the
+// factorisation (every rank applies each broadcast panel to its copy on a side stream), so B holds L^-1 P B on return
+// and *rode is set; otherwise B is not touched.
+int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv, double* B = nullptr, int64_t ldb = 0,
+                 int64_t nrhs = 0, bool* rode = nullptr);
 // op(T) X = B for a block-cyclic triangular factor and B (Np x nrhs, ldb) replicated on every rank
 int pdtrsv_rank(Rank& R, int64_t Np, int64_t nb, const double* T, int64_t lld, bool upper, bool trans, bool unit,
                 double* B, int64_t ldb, int64_t nrhs);

@@ -266,13 +266,16 @@ static int pdgesv_host(int64_t n, int64_t nrhs, double* a, int64_t lda, fint* ip
       if (n < Np) LLA_CUDA(cudaMemsetAsync(B.p, 0, (size_t)Np * nrhs * 8, st));
       LLA_TRY(stage_region_h2d(B.p, (size_t)Np * 8, b, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, st));
     }
-    LLA_TRY(pdgetrf_rank(R, Np, nb, (double*)A.p, mloc, (int*)piv.p));
+    bool rode = false;   // the forward substitution rode along with the factorisation (block columns)
+    LLA_TRY(pdgetrf_rank(R, Np, nb, (double*)A.p, mloc, (int*)piv.p, nrhs > 0 ? (double*)B.p : nullptr, Np, nrhs, &rode));
     int info = 0;
     LLA_TRY(finish_info(R, &info));
     infos[(size_t)R.rank] = info;
     if (info == 0 && nrhs > 0) {
-      LLA_TRY(pdlaswp_rhs_rank(R, Np, (const int*)piv.p, (double*)B.p, Np, nrhs));
-      LLA_TRY(pdtrsv_rank(R, Np, nb, (const double*)A.p, mloc, false, false, true, (double*)B.p, Np, nrhs));
+      if (!rode) {
+        LLA_TRY(pdlaswp_rhs_rank(R, Np, (const int*)piv.p, (double*)B.p, Np, nrhs));
+        LLA_TRY(pdtrsv_rank(R, Np, nb, (const double*)A.p, mloc, false, false, true, (double*)B.p, Np, nrhs));
+      }
       LLA_TRY(pdtrsv_rank(R, Np, nb, (const double*)A.p, mloc, true, false, false, (double*)B.p, Np, nrhs));
       if (R.rank == 0) LLA_TRY(stage_region_d2h(b, (size_t)ldb * 8, B.p, (size_t)Np * 8, (size_t)n * 8, (size_t)nrhs, st));
     }
@@ -539,6 +542,25 @@ int llacuda_pdgetrf_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* i
   return run_ranks([&](Rank& R) -> int {
     LLA_TRY(pdgetrf_rank(R, Np, nb, A, lld, ipiv_dev));
     return finish_info(R, info);
+  });
+}
+/* factorisation and solve in one call: B (Np x nrhs, ldb, replicated on every rank) is overwritten by X when *info == 0
+   and holds garbage otherwise (the caller keeps the original, as LLA does); on block columns the forward substitution
+   rides along with the factorisation */
+int llacuda_pdgesv_local(int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv_dev, double* B, int64_t ldb, int64_t nrhs,
+                         int* info) {
+  ApiLock api_lock;
+  if (local_rank("llacuda_pdgesv_local")) return LLACUDA_ERR_BAD_ARG;
+  return run_ranks([&](Rank& R) -> int {
+    bool rode = false;
+    LLA_TRY(pdgetrf_rank(R, Np, nb, A, lld, ipiv_dev, nrhs > 0 ? B : nullptr, ldb, nrhs, &rode));
+    LLA_TRY(finish_info(R, info));
+    if (*info != 0 || nrhs <= 0) return 0;
+    if (!rode) {
+      LLA_TRY(pdlaswp_rhs_rank(R, Np, ipiv_dev, B, ldb, nrhs));
+      LLA_TRY(pdtrsv_rank(R, Np, nb, A, lld, false, false, true, B, ldb, nrhs));
+    }
+    return pdtrsv_rank(R, Np, nb, A, lld, true, false, false, B, ldb, nrhs);
   });
 }
 /* B: Np x nrhs (ldb) replicated on every rank, overwritten by X */

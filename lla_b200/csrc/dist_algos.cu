@@ -514,7 +514,8 @@ __global__ void __launch_bounds__(256) lla_swap_unpack_kernel(double* __restrict
 
 }  // namespace
 
-int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv) {
+int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* ipiv, double* B, int64_t ldb, int64_t nrhs,
+                 bool* rode) {
   const NcclApi* nc = nccl();
   const int P = R.P, Q = R.Q, p = R.p, q = R.q;
   if (Np % (nb * lcm(P, Q)) || nb % IB || 2 * nb > LSW_MAX) {
@@ -544,6 +545,12 @@ int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* i
   LLA_CUDA(cudaEventRecord(ev_start, R.main));
   LLA_CUDA(cudaStreamWaitEvent(R.side, ev_start, 0));
   cudaStream_t sd = R.side;
+  // right-hand sides riding along (block columns only: every rank sees whole rows of the broadcast panel)
+  const bool rider = B != nullptr && nrhs > 0 && P == 1 && getenv("LLACUDA_LU_NO_RHS_RIDER") == nullptr;
+  cudaEvent_t ev_rider[2] = {R.ev[4], R.ev[5]};
+  cudaStream_t sB = R.chain;
+  if (rider) LLA_CUDA(cudaStreamWaitEvent(sB, ev_start, 0));
+  if (rode) *rode = rider;
 
   auto panel = [&](int64_t k) -> int {
     const int slot = (int)(k & 1);
@@ -552,6 +559,7 @@ int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* i
     double* PN = (double*)pan[slot].p;
     int* piv = (int*)pivb[slot].p;
     const int root = pk * Q + qk;
+    if (rider && k >= 2) LLA_CUDA(cudaStreamWaitEvent(sd, ev_rider[slot], 0));   // the rider of panel k - 2 read this slot
     if (q == qk) {
       const int64_t lkc = k / Q;
       double* col = A + lkc * nb * lld;                  // my rows of block column k
@@ -627,6 +635,15 @@ int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* i
     }
     LLA_CUDA(cudaGetLastError());
     LLA_CUDA(cudaEventRecord(ev_panel[slot], sd));
+    if (rider) {
+      // interchanges of this panel, solve with its unit-lower triangle, product with the rows below -- on my copy of B
+      double* Bk = B + k * nb;
+      LLA_CUDA(cudaStreamWaitEvent(sB, ev_panel[slot], 0));
+      LLA_TRY(dlaswp_dev(nrhs, Bk, ldb, 0, nb, piv, true, sB));
+      LLA_TRY(dtrsm_left_inv_dev(false, 0, nb, nrhs, PN, mk, (const double*)linv[slot].p, Bk, ldb, sB));
+      if (mk > nb) LLA_TRY(dgemm_dev(0, 0, mk - nb, nrhs, nb, -1.0, PN + nb, mk, Bk, ldb, 1.0, Bk + nb, ldb, TRI_FULL, sB));
+      LLA_CUDA(cudaEventRecord(ev_rider[slot], sB));
+    }
     return 0;
   };
 
@@ -712,6 +729,10 @@ int pdgetrf_rank(Rank& R, int64_t Np, int64_t nb, double* A, int64_t lld, int* i
   }
   LLA_CUDA(cudaEventRecord(ev_start, sd));
   LLA_CUDA(cudaStreamWaitEvent(R.main, ev_start, 0));
+  if (rider) {
+    LLA_CUDA(cudaEventRecord(ev_start, sB));
+    LLA_CUDA(cudaStreamWaitEvent(R.main, ev_start, 0));
+  }
   LLA_CUDA(cudaStreamSynchronize(R.main));
   return 0;
 }

@@ -163,6 +163,14 @@ def pdgetrf_local(Np, nb, A, lld, ipiv_dev) -> int:
     return inf.value
 
 
+def pdgesv_local(Np, nb, A, lld, ipiv_dev, B, ldb, nrhs) -> int:
+    """factorisation + solve on device-resident block-cyclic A and replicated B (X on return when the INFO returned is 0)"""
+    inf = _int(0)
+    f = _f("llacuda_pdgesv_local", [_i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, ctypes.POINTER(_int)])
+    _lib.check(f(Np, nb, A, lld, ipiv_dev, B, ldb, nrhs, inf), "pdgesv_local")
+    return inf.value
+
+
 def pdgetrs_local(Np, nb, LU, lld, ipiv_dev, B, ldb, nrhs):
     f = _f("llacuda_pdgetrs_local", [_i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64])
     _lib.check(f(Np, nb, LU, lld, ipiv_dev, B, ldb, nrhs), "pdgetrs_local")

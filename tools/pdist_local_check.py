@@ -71,6 +71,20 @@ def main():
             x = Bd.cpu().numpy().T
             res = np.linalg.norm(a @ x - rhs) / (n * EPS * np.linalg.norm(a) * np.linalg.norm(x))
             assert res <= 10, ("pdgetrs", P, Q, res)
+        # ---- the same system through the one-call entry point (right-hand sides ride along on block columns)
+        A2 = torch.as_tensor(bc.scatter(np.ascontiguousarray(a.T)), device=dev)
+        ipiv2 = torch.zeros(n, dtype=torch.int32, device=dev)
+        B2 = torch.as_tensor(np.ascontiguousarray(rhs.T), device=dev)
+        torch.cuda.synchronize()
+        info = PD.pdgesv_local(n, nb, A2.data_ptr(), bc.mloc, ipiv2.data_ptr(), B2.data_ptr(), n, 3)
+        torch.cuda.synchronize()
+        assert info == 0
+        assert torch.equal(ipiv2, ipiv) and torch.equal(A2, A), ("pdgesv_local factors", P, Q)
+        if rank == 0:
+            x2 = B2.cpu().numpy().T
+            res = np.linalg.norm(a @ x2 - rhs) / (n * EPS * np.linalg.norm(a) * np.linalg.norm(x2))
+            assert res <= 10, ("pdgesv_local", P, Q, res)
+            assert np.max(np.abs(x2 - x)) <= 1e4 * n * EPS * np.abs(x).max(), ("pdgesv_local vs pdgetrs", P, Q)
         # ---- Cholesky + solve
         g = rng.uniform(0, 1, (n, n))
         s = g @ g.T + n * np.eye(n)
