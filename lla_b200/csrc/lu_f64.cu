@@ -562,7 +562,17 @@ static int lu_leaf(const LuCtx& L, int64_t j0, int64_t m, int w) {
   }
   static const bool leaf_trace = getenv("LLACUDA_TRACE_LEAF") != nullptr;
   if (leaf_trace) trace_mark(L.st, "lu.leaf>", j0, m);
-  const int pr = L.pr ? L.pr : panel_rows();
+  int pr = L.pr ? L.pr : panel_rows();
+  {
+    // co-residency of the cooperative launch (launch bounds: 3 / 2 / 1 CTAs per SM for 128 / 256 / 512 rows; the measured
+    // occupancy of the default height is in L.per_sm): taller CTAs when the panel does not fit
+    const int64_t sms = ctx()->sm_count;
+    auto fits = [&](int rows) {
+      const int64_t per = rows == panel_rows() ? L.per_sm : (rows == 128 ? 3 : (rows == 256 ? 2 : 1));
+      return (m + rows - 1) / rows <= per * sms;
+    };
+    while (pr < 512 && !fits(pr)) pr *= 2;
+  }
   if (pr == 128) LLA_TRY(launch_panel<128>(L, P, m, w, j0, epoch, dbg));
   else if (pr == 256) LLA_TRY(launch_panel<256>(L, P, m, w, j0, epoch, dbg));
   else LLA_TRY(launch_panel<512>(L, P, m, w, j0, epoch, dbg));
@@ -960,7 +970,9 @@ int dgetrf_dev(int64_t m, int64_t n, double* A, int64_t lda, int* ipiv, int* inf
       LLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lla_dgetf2_panel_kernel<512, false>, 512, panel_smem<512>()));
     }
   }
-  if ((int64_t)per_sm * c->sm_count < maxG) {
+  // a panel taller than the co-residency bound of the default CTA height runs with taller CTAs (lu_leaf escalates);
+  // only beyond 512 rows per CTA x one CTA per SM there is no cooperative launch left
+  if ((m + 511) / 512 > (int64_t)c->sm_count) {
     set_error(__FILE__, __LINE__, "dgetrf: panel too tall for one cooperative launch", (int)m);
     return LLACUDA_ERR_BAD_ARG;
   }

@@ -3,14 +3,15 @@ import sys, os, torch
 sys.path.insert(0, ".")
 from lla_b200 import _lib, device as D
 _lib.init(0); D.use_torch_stream()
-for n in (8192, 16384):
-    nrhs = 64
+sizes = [int(v) for v in sys.argv[1:]] or [8192, 16384]
+for n in sizes:
+    nrhs = 64 if n <= 32768 else 2
     A0 = torch.rand((n, n), dtype=torch.float64, device="cuda") * 10      # column-major image: A0[j, i] = a_ij
     B0 = torch.rand((nrhs, n), dtype=torch.float64, device="cuda") * 10
     A, B = A0.clone(), B0.clone()
     ipiv = torch.zeros(n, dtype=torch.int32, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
     best = 1e9
-    for _ in range(3):
+    for _ in range(3 if n <= 32768 else 1):
         A.copy_(A0); B.copy_(B0); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); D.dgesv(n, nrhs, A.data_ptr(), n, ipiv.data_ptr(), B.data_ptr(), n, info.data_ptr()); e1.record()
